@@ -1,0 +1,729 @@
+/*
+ * ORACLE (test infrastructure) -- CPU restatement of the subset of DVODE_F90
+ * that UCLCHEM executes: METH=2 (BDF), MITER=2 (dense finite-difference
+ * Jacobian), JSV=+1 (saved Jacobian copy), ITASK=1, ISTATE=1 on every call,
+ * ITOL=2 (scalar rtol, vector atol), no bounds, no root finding.
+ * Follows reference src/fortran_src/dvode.f90:
+ *   driver      DVODE        :5654-6766      DVHIN   :6768-6898
+ *   DVINDY_CORE :6901-6989   DVSTEP  :7180-7613   DVSET  :7616-7787
+ *   DVJUST      :7790-7923   DVNLSD  :7926-8179   DVJAC  :8182-8400 (MITER=2 FD branch :8331-8352)
+ *   DVSOL       :8698        DEWSET  :8981        DVNORM :9021
+ *   DGEFA/DGESL :11982-12204 (LINPACK LU with partial pivoting)
+ * Constants: dvode.f90:1875-1911.
+ */
+#include "orc_vode.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ADDON 1.0e-6
+#define BIAS1 6.0
+#define BIAS2 6.0
+#define BIAS3 10.0
+#define CCMAX 0.3
+#define CORTES 0.1
+#define CRDOWN 0.3
+#define ETACF 0.25
+#define ETAMIN 0.1
+#define ETAMX1 1.0e4
+#define ETAMX2 10.0
+#define ETAMX3 10.0
+#define ETAMXF 0.2
+#define ONEPSM 1.00001
+#define RDIV 2.0
+#define THRESH 1.5
+#define KFC (-3)
+#define KFH (-15)
+#define MAXCOR 3
+#define MSBP 20
+#define MXNCF 10
+#define MAXORD 5
+
+vode_t *vode_alloc(int n)
+{
+    vode_t *s = (vode_t *)calloc(1, sizeof(vode_t));
+    s->n = n;
+    s->yh = (double *)calloc((size_t)(MAXORD + 1) * n, sizeof(double));
+    s->ewt = (double *)calloc(n, sizeof(double));
+    s->savf = (double *)calloc(n, sizeof(double));
+    s->acor = (double *)calloc(n, sizeof(double));
+    s->y = (double *)calloc(n, sizeof(double));
+    s->ftem = (double *)calloc(n, sizeof(double));
+    s->wm = (double *)calloc((size_t)n * n, sizeof(double));
+    s->jsv = (double *)calloc((size_t)n * n, sizeof(double));
+    s->ipvt = (int *)calloc(n, sizeof(int));
+    return s;
+}
+
+void vode_free(vode_t *s)
+{
+    if (!s) return;
+    free(s->yh); free(s->ewt); free(s->savf); free(s->acor); free(s->y);
+    free(s->ftem); free(s->wm); free(s->jsv); free(s->ipvt); free(s);
+}
+
+/* DVNORM dvode.f90:9021 */
+static double vnorm(int n, const double *v, const double *w)
+{
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) {
+        double t = v[i] * w[i];
+        sum += t * t;
+    }
+    return sqrt(sum / (double)n);
+}
+
+/* DEWSET dvode.f90:8981 (ITOL=2) followed by the reciprocal of :6259-6263 */
+static int ewset(vode_t *s, const double *ycur)
+{
+    for (int i = 0; i < s->n; i++) {
+        double e = s->rtol * fabs(ycur[i]) + s->atol[i];
+        if (e <= 0.0) return -1;
+        s->ewt[i] = 1.0 / e;
+    }
+    return 0;
+}
+
+/* DGEFA_F90 dvode.f90:11982 -- column-major a[i + j*n] */
+static int dgefa(double *a, int n, int *ipvt)
+{
+    int info = 0;
+    for (int k = 0; k < n - 1; k++) {
+        double *ak = a + (size_t)k * n;
+        int l = k;
+        double dmax = fabs(ak[k]);
+        for (int i = k + 1; i < n; i++)
+            if (fabs(ak[i]) > dmax) { dmax = fabs(ak[i]); l = i; }
+        ipvt[k] = l;
+        if (ak[l] == 0.0) { info = k + 1; continue; }
+        if (l != k) { double t = ak[l]; ak[l] = ak[k]; ak[k] = t; }
+        double t = -1.0 / ak[k];
+        for (int i = k + 1; i < n; i++) ak[i] *= t;
+        for (int j = k + 1; j < n; j++) {
+            double *aj = a + (size_t)j * n;
+            double tj = aj[l];
+            if (l != k) { aj[l] = aj[k]; aj[k] = tj; }
+            if (tj != 0.0)
+                for (int i = k + 1; i < n; i++) aj[i] += tj * ak[i];
+        }
+    }
+    ipvt[n - 1] = n - 1;
+    if (a[(size_t)(n - 1) * n + (n - 1)] == 0.0) info = n;
+    return info;
+}
+
+/* DGESL_F90 dvode.f90:12091 (JOB=0) */
+static void dgesl(const double *a, int n, const int *ipvt, double *b)
+{
+    for (int k = 0; k < n - 1; k++) {
+        int l = ipvt[k];
+        double t = b[l];
+        if (l != k) { b[l] = b[k]; b[k] = t; }
+        const double *ak = a + (size_t)k * n;
+        if (t != 0.0)
+            for (int i = k + 1; i < n; i++) b[i] += t * ak[i];
+    }
+    for (int kb = 0; kb < n; kb++) {
+        int k = n - 1 - kb;
+        const double *ak = a + (size_t)k * n;
+        b[k] /= ak[k];
+        double t = -b[k];
+        if (t != 0.0)
+            for (int i = 0; i < k; i++) b[i] += t * ak[i];
+    }
+}
+
+/* DVHIN dvode.f90:6768 */
+static int vhin(vode_t *s, double t0, const double *y0, const double *ydot, double tout, double *h0,
+                int *niter)
+{
+    int n = s->n;
+    double *y = s->y, *temp = s->acor;
+    *niter = 0;
+    double tdist = fabs(tout - t0);
+    double tround = s->uround * fmax(fabs(t0), fabs(tout));
+    if (tdist < 2.0 * tround) return -1;
+    double hlb = 100.0 * tround;
+    double hub = 0.1 * tdist;
+    for (int i = 0; i < n; i++) {
+        double delyi = 0.1 * fabs(y0[i]) + s->atol[i];
+        double afi = fabs(ydot[i]);
+        if (afi * hub > delyi) hub = delyi / afi;
+    }
+    int iter = 0;
+    double hg = sqrt(hlb * hub);
+    double hnew;
+    if (hub < hlb) {
+        *h0 = copysign(hg, tout - t0);
+        *niter = iter;
+        return 0;
+    }
+    for (;;) {
+        double h = copysign(hg, tout - t0);
+        double t1 = t0 + h;
+        for (int i = 0; i < n; i++) y[i] = y0[i] + h * ydot[i];
+        s->f(s->ctx, t1, y, temp);
+        s->nfe++;
+        for (int i = 0; i < n; i++) temp[i] = (temp[i] - ydot[i]) / h;
+        double yddnrm = vnorm(n, temp, s->ewt);
+        if (yddnrm * hub * hub > 2.0)
+            hnew = sqrt(2.0 / yddnrm);
+        else
+            hnew = sqrt(hg * hub);
+        iter++;
+        if (iter >= 4) break;
+        double hrat = hnew / hg;
+        if (hrat > 0.5 && hrat < 2.0) break;
+        if (iter >= 2 && hnew > 2.0 * hg) { hnew = hg; break; }
+        hg = hnew;
+    }
+    double h = hnew * 0.5;
+    if (h < hlb) h = hlb;
+    if (h > hub) h = hub;
+    *h0 = copysign(h, tout - t0);
+    /* NB DVHIN increments NFE itself and the driver adds NITER again (:6273);
+     * keep the driver's accounting only. */
+    s->nfe -= iter;
+    *niter = iter;
+    return 0;
+}
+
+/* DVSET dvode.f90:7616, BDF branch :7739-7786.  Arrays are 1-based like the Fortran. */
+static void vset(vode_t *s)
+{
+    double *el = s->el, *tq = s->tq, *tau = s->tau;
+    int nq = s->nq, l = s->l;
+    double flotl = (double)l;
+    int nqm1 = nq - 1, nqm2 = nq - 2;
+    for (int i = 3; i <= l; i++) el[i] = 0.0;
+    el[1] = 1.0;
+    el[2] = 1.0;
+    double alph0 = -1.0, ahatn0 = -1.0, hsum = s->h, rxi = 1.0, rxis = 1.0;
+    if (nq != 1) {
+        for (int j = 1; j <= nqm2; j++) {
+            hsum += tau[j];
+            rxi = s->h / hsum;
+            int jp1 = j + 1;
+            alph0 -= 1.0 / (double)jp1;
+            for (int iback = 1; iback <= jp1; iback++) {
+                int i = (j + 3) - iback;
+                el[i] = el[i] + el[i - 1] * rxi;
+            }
+        }
+        alph0 -= 1.0 / (double)nq;
+        rxis = -el[2] - alph0;
+        hsum += tau[nqm1];
+        rxi = s->h / hsum;
+        ahatn0 = -el[2] - rxi;
+        for (int iback = 1; iback <= nq; iback++) {
+            int i = (nq + 2) - iback;
+            el[i] = el[i] + el[i - 1] * rxis;
+        }
+    }
+    double t1 = 1.0 - ahatn0 + alph0;
+    double t2 = 1.0 + (double)nq * t1;
+    tq[2] = fabs(alph0 * t2 / t1);
+    tq[5] = fabs(t2 / (el[l] * rxi / rxis));
+    if (s->nqwait == 1) {
+        double cnqm1 = rxis / el[l];
+        double t3 = alph0 + 1.0 / (double)nq;
+        double t4 = ahatn0 + rxi;
+        double elp = t3 / (1.0 - t4 + t3);
+        tq[1] = fabs(elp / cnqm1);
+        hsum += tau[nq];
+        rxi = s->h / hsum;
+        double t5 = alph0 - 1.0 / (double)(nq + 1);
+        double t6 = ahatn0 - rxi;
+        elp = t2 / (1.0 - t6 + t5);
+        tq[3] = fabs(elp * rxi * (flotl + 1.0) * t5);
+    }
+    tq[4] = CORTES * tq[2];
+}
+
+#define YH(j) (s->yh + (size_t)((j)-1) * s->n) /* 1-based column j */
+
+/* DVJUST dvode.f90:7790, BDF branch :7862-7921 */
+static void vjust(vode_t *s, int iord)
+{
+    int n = s->n, nq = s->nq, l = s->l, lmax = s->lmax;
+    double *el = s->el, *tau = s->tau;
+    if (nq == 2 && iord != 1) return;
+    int nqm1 = nq - 1, nqm2 = nq - 2;
+    if (iord != 1) {
+        for (int i = 1; i <= lmax; i++) el[i] = 0.0;
+        el[3] = 1.0;
+        double hsum = 0.0;
+        for (int j = 1; j <= nqm2; j++) {
+            hsum += tau[j];
+            double xi = hsum / s->hscal;
+            int jp1 = j + 1;
+            for (int iback = 1; iback <= jp1; iback++) {
+                int i = (j + 4) - iback;
+                el[i] = el[i] * xi + el[i - 1];
+            }
+        }
+        for (int j = 3; j <= nq; j++) {
+            double *yj = YH(j), *yl = YH(l);
+            for (int i = 0; i < n; i++) yj[i] = yj[i] - yl[i] * el[j];
+        }
+        return;
+    }
+    for (int i = 1; i <= lmax; i++) el[i] = 0.0;
+    el[3] = 1.0;
+    double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0, hsum = s->hscal;
+    if (nq != 1) {
+        for (int j = 1; j <= nqm1; j++) {
+            int jp1 = j + 1;
+            hsum += tau[jp1];
+            double xi = hsum / s->hscal;
+            prod *= xi;
+            alph0 -= 1.0 / (double)jp1;
+            alph1 += 1.0 / xi;
+            for (int iback = 1; iback <= jp1; iback++) {
+                int i = (j + 4) - iback;
+                el[i] = el[i] * xiold + el[i - 1];
+            }
+            xiold = xi;
+        }
+    }
+    double t1 = (-alph0 - alph1) / prod;
+    int lp1 = l + 1;
+    double *ylp1 = YH(lp1), *ylmax = YH(lmax);
+    for (int i = 0; i < n; i++) ylp1[i] = t1 * ylmax[i];
+    int nqp1 = nq + 1;
+    for (int j = 3; j <= nqp1; j++) {
+        double *yj = YH(j);
+        for (int i = 0; i < n; i++) yj[i] += el[j] * ylp1[i];
+    }
+}
+
+/* DVJAC dvode.f90:8182 (MITER=2, JSV=1, not JACSP) */
+static int vjac(vode_t *s)
+{
+    int n = s->n;
+    size_t lenp = (size_t)n * n;
+    double hrl1 = s->h * s->rl1;
+    int jok = 1;
+    if (s->nst == 0 || s->nst > s->nslj + s->msbj) jok = -1;
+    if (s->icf == 1 && s->drc < s->ccmxj) jok = -1;
+    if (s->icf == 2) jok = -1;
+    if (jok == -1) {
+        s->nslj = s->nst;
+        s->jcur = 1;
+        double fac = vnorm(n, s->savf, s->ewt);
+        double r0 = 1000.0 * fabs(s->h) * s->uround * (double)n * fac;
+        if (fabs(r0) <= 0.0) r0 = 1.0;
+        double srur = sqrt(s->uround);
+        for (int j = 0; j < n; j++) {
+            double yj = s->y[j];
+            double r = fmax(srur * fabs(yj), r0 / s->ewt[j]);
+            s->y[j] += r;
+            fac = 1.0 / r;
+            s->f(s->ctx, s->tn, s->y, s->ftem);
+            double *col = s->wm + (size_t)j * n;
+            for (int i = 0; i < n; i++) col[i] = (s->ftem[i] - s->savf[i]) * fac;
+            s->y[j] = yj;
+        }
+        s->nfe += n;
+        s->nje++;
+        memcpy(s->jsv, s->wm, lenp * sizeof(double));
+    } else {
+        s->jcur = 0;
+        memcpy(s->wm, s->jsv, lenp * sizeof(double));
+    }
+    double con = -hrl1;
+    for (size_t i = 0; i < lenp; i++) s->wm[i] *= con;
+    for (int i = 0; i < n; i++) s->wm[(size_t)i * n + i] += 1.0;
+    s->nlu++;
+    int ier = dgefa(s->wm, n, s->ipvt);
+    return ier != 0 ? 1 : 0;
+}
+
+/* DVNLSD dvode.f90:7926 */
+static int vnls(vode_t *s, int *nflag)
+{
+    int n = s->n;
+    double *y = s->y, *savf = s->savf, *acor = s->acor, *yh1 = YH(1), *yh2 = YH(2);
+    if (s->jstart == 0) s->nslp = 0;
+    if (*nflag == 0) s->icf = 0;
+    if (*nflag == -2) s->ipup = 2;
+    if (s->jstart == 0 || s->jstart == -1) s->ipup = 2;
+    s->drc = fabs(s->rc - 1.0);
+    if (s->drc > CCMAX || s->nst >= s->nslp + MSBP) s->ipup = 2;
+    for (;;) { /* label 10 */
+        int m = 0;
+        double delp = 0.0, del = 0.0;
+        memcpy(y, yh1, n * sizeof(double));
+        s->f(s->ctx, s->tn, y, savf);
+        s->nfe++;
+        if (s->ipup > 0) {
+            int ierpj = vjac(s);
+            s->ipup = 0;
+            s->rc = 1.0;
+            s->drc = 0.0;
+            s->crate = 1.0;
+            s->nslp = s->nst;
+            if (ierpj != 0) goto fail70;
+        }
+        for (int i = 0; i < n; i++) acor[i] = 0.0;
+        for (;;) { /* label 30/40 */
+            for (int i = 0; i < n; i++)
+                y[i] = (s->rl1 * s->h) * savf[i] - (s->rl1 * yh2[i] + acor[i]);
+            dgesl(s->wm, n, s->ipvt, y);
+            s->nni++;
+            if (fabs(s->rc - 1.0) > 0.0) {
+                double cscale = 2.0 / (1.0 + s->rc);
+                for (int i = 0; i < n; i++) y[i] *= cscale;
+            }
+            del = vnorm(n, y, s->ewt);
+            for (int i = 0; i < n; i++) acor[i] += y[i];
+            for (int i = 0; i < n; i++) y[i] = yh1[i] + acor[i];
+            if (m != 0) s->crate = fmax(CRDOWN * s->crate, del / delp);
+            double dcon = del * fmin(1.0, s->crate) / s->tq[4];
+            if (dcon <= 1.0) { /* label 80 */
+                *nflag = 0;
+                s->jcur = 0;
+                s->icf = 0;
+                s->acnrm = (m == 0) ? del : vnorm(n, acor, s->ewt);
+                return 0;
+            }
+            m++;
+            if (m == MAXCOR) break;
+            if (m >= 2 && del > RDIV * delp) break;
+            delp = del;
+            s->f(s->ctx, s->tn, y, savf);
+            s->nfe++;
+        }
+        /* label 60 */
+        if (s->jcur == 1) goto fail70;
+        s->icf = 1;
+        s->ipup = 2;
+    }
+fail70:
+    *nflag = -1;
+    s->icf = 2;
+    s->ipup = 2;
+    return -1;
+}
+
+static void predict(vode_t *s, int sign)
+{
+    /* Pascal-triangle update of the Nordsieck array, dvode.f90:7367-7375 / :7396-7402 */
+    int n = s->n, nq = s->nq;
+    double *yh1 = s->yh;
+    long nqnyh = (long)nq * n;
+    long i1 = nqnyh + 1;
+    for (int jb = 1; jb <= nq; jb++) {
+        i1 -= n;
+        if (sign > 0)
+            for (long i = i1; i <= nqnyh; i++) yh1[i - 1] += yh1[i - 1 + n];
+        else
+            for (long i = i1; i <= nqnyh; i++) yh1[i - 1] -= yh1[i - 1 + n];
+    }
+}
+
+static void rescale(vode_t *s)
+{
+    /* label 60 of DVSTEP, dvode.f90:7355-7363 */
+    int n = s->n;
+    double r = 1.0;
+    for (int j = 2; j <= s->l; j++) {
+        r *= s->eta;
+        double *yj = YH(j);
+        for (int i = 0; i < n; i++) yj[i] *= r;
+    }
+    s->h = s->hscal * s->eta;
+    s->hscal = s->h;
+    s->rc = s->rc * s->eta;
+}
+
+/* DVSTEP dvode.f90:7180 */
+static void vstep(vode_t *s)
+{
+    int n = s->n;
+    double told = s->tn;
+    int ncf = 0, nflag = 0;
+    s->kflag = 0;
+    s->jcur = 0;
+    double dsm = 0.0;
+    int do_rescale = 0;
+
+    if (s->jstart > 0) {
+        /* label 10/20 */
+        if (s->newh != 0) {
+            if (s->newq < s->nq) {
+                vjust(s, -1);
+                s->nq = s->newq;
+                s->l = s->nq + 1;
+                s->nqwait = s->l;
+            } else if (s->newq > s->nq) {
+                vjust(s, 1);
+                s->nq = s->newq;
+                s->l = s->nq + 1;
+                s->nqwait = s->l;
+            }
+            do_rescale = 1;
+        }
+    } else {
+        /* JSTART == 0: first call */
+        s->lmax = MAXORD + 1;
+        s->nq = 1;
+        s->l = 2;
+        s->tau[1] = s->h;
+        s->prl1 = 1.0;
+        s->rc = 0.0;
+        s->etamax = ETAMX1;
+        s->nqwait = 2;
+        s->hscal = s->h;
+    }
+
+    for (;;) {
+        if (do_rescale) rescale(s);
+        do_rescale = 0;
+        /* label 70 */
+        s->tn += s->h;
+        predict(s, +1);
+        vset(s);
+        s->rl1 = 1.0 / s->el[2];
+        s->rc = s->rc * (s->rl1 / s->prl1);
+        s->prl1 = s->rl1;
+
+        vnls(s, &nflag);
+
+        if (nflag != 0) {
+            ncf++;
+            s->ncfn++;
+            s->etamax = 1.0;
+            s->tn = told;
+            predict(s, -1);
+            if (nflag < -1) { s->kflag = (nflag == -2) ? -3 : -4; goto done260; }
+            if (fabs(s->h) <= s->hmin * ONEPSM) { s->kflag = -2; goto done260; }
+            if (ncf == MXNCF) { s->kflag = -2; goto done260; }
+            s->eta = ETACF;
+            s->eta = fmax(s->eta, s->hmin / fabs(s->h));
+            nflag = -1;
+            do_rescale = 1;
+            continue;
+        }
+        /* label 80: error test */
+        dsm = s->acnrm / s->tq[2];
+        if (dsm <= 1.0) break;
+        /* label 100 */
+        s->kflag--;
+        s->netf++;
+        nflag = -2;
+        s->tn = told;
+        predict(s, -1);
+        if (fabs(s->h) <= s->hmin * ONEPSM) { s->kflag = -1; goto done260; }
+        s->etamax = 1.0;
+        if (s->kflag > KFC) {
+            double flotl = (double)s->l;
+            s->eta = 1.0 / (pow(BIAS2 * dsm, 1.0 / flotl) + ADDON);
+            s->eta = fmax(s->eta, fmax(s->hmin / fabs(s->h), ETAMIN));
+            if (s->kflag <= -2 && s->eta > ETAMXF) s->eta = ETAMXF;
+            do_rescale = 1;
+            continue;
+        }
+        /* label 110 */
+        if (s->kflag == KFH) { s->kflag = -1; goto done260; }
+        if (s->nq != 1) {
+            s->eta = fmax(ETAMIN, s->hmin / fabs(s->h));
+            vjust(s, -1);
+            s->l = s->nq;
+            s->nq = s->nq - 1;
+            s->nqwait = s->l;
+            do_rescale = 1;
+            continue;
+        }
+        /* label 120 */
+        s->eta = fmax(ETAMIN, s->hmin / fabs(s->h));
+        s->h = s->h * s->eta;
+        s->hscal = s->h;
+        s->tau[1] = s->h;
+        s->f(s->ctx, s->tn, s->y, s->savf);
+        s->nfe++;
+        {
+            double *yh2 = YH(2);
+            for (int i = 0; i < n; i++) yh2[i] = s->h * s->savf[i];
+        }
+        s->nqwait = 10;
+        /* GOTO 70 without rescale */
+    }
+
+    /* successful step */
+    s->kflag = 0;
+    s->nst++;
+    s->hu = s->h;
+    s->nqu = s->nq;
+    for (int iback = 1; iback <= s->nq; iback++) {
+        int i = s->l - iback;
+        s->tau[i + 1] = s->tau[i];
+    }
+    s->tau[1] = s->h;
+    for (int j = 1; j <= s->l; j++) {
+        double *yj = YH(j);
+        double e = s->el[j];
+        for (int i = 0; i < n; i++) yj[i] += e * s->acor[i];
+    }
+    s->nqwait--;
+    if (s->l != s->lmax && s->nqwait == 1) {
+        memcpy(YH(s->lmax), s->acor, n * sizeof(double));
+        s->conp = s->tq[5];
+    }
+    if (fabs(s->etamax - 1.0) > 0.0) {
+        /* label 130 */
+        double flotl = (double)s->l;
+        double etaq = 1.0 / (pow(BIAS2 * dsm, 1.0 / flotl) + ADDON);
+        int choose = 0; /* 0 same order, -1 down, +1 up */
+        if (s->nqwait != 0) {
+            choose = 0;
+        } else {
+            s->nqwait = 2;
+            double etaqm1 = 0.0, etaqp1 = 0.0;
+            if (s->nq != 1) {
+                double ddn = vnorm(n, YH(s->l), s->ewt) / s->tq[1];
+                etaqm1 = 1.0 / (pow(BIAS1 * ddn, 1.0 / (flotl - 1.0)) + ADDON);
+            }
+            if (s->l != s->lmax) {
+                double cnquot = (s->tq[5] / s->conp) * pow(s->h / s->tau[2], (double)s->l);
+                double *ylmax = YH(s->lmax);
+                for (int i = 0; i < n; i++) s->savf[i] = s->acor[i] - cnquot * ylmax[i];
+                double dup = vnorm(n, s->savf, s->ewt) / s->tq[3];
+                etaqp1 = 1.0 / (pow(BIAS3 * dup, 1.0 / (flotl + 1.0)) + ADDON);
+            }
+            if (etaq >= etaqp1) {
+                if (etaq < etaqm1) choose = -1; else choose = 0;
+            } else {
+                if (etaqp1 > etaqm1) choose = 1; else choose = -1;
+            }
+            if (choose == -1) { s->eta = etaqm1; s->newq = s->nq - 1; }
+            if (choose == 1) {
+                s->eta = etaqp1;
+                s->newq = s->nq + 1;
+                memcpy(YH(s->lmax), s->acor, n * sizeof(double));
+            }
+        }
+        if (choose == 0) { s->eta = etaq; s->newq = s->nq; }
+        /* label 200 */
+        if (s->eta < THRESH || fabs(s->etamax - 1.0) <= 0.0) {
+            s->newq = s->nq;
+            s->newh = 0;
+            s->eta = 1.0;
+            s->hnew = s->h;
+        } else {
+            s->eta = fmin(s->eta, s->etamax);
+            s->eta = s->eta / fmax(1.0, fabs(s->h) * s->hmxi * s->eta);
+            s->newh = 1;
+            s->hnew = s->h * s->eta;
+        }
+    } else {
+        if (s->nqwait < 2) s->nqwait = 2;
+        s->newq = s->nq;
+        s->newh = 0;
+        s->eta = 1.0;
+        s->hnew = s->h;
+    }
+    /* label 250 */
+    s->etamax = ETAMX3;
+    if (s->nst <= 10) s->etamax = ETAMX2;
+    {
+        double r = 1.0 / s->tq[2];
+        for (int i = 0; i < n; i++) s->acor[i] *= r;
+    }
+done260:
+    s->jstart = 1;
+}
+
+/* DVINDY_CORE dvode.f90:6901 with K=0 */
+static int vindy(vode_t *s, double t, double *dky)
+{
+    int n = s->n;
+    double tfuzz = 100.0 * s->uround * copysign(fabs(s->tn) + fabs(s->hu), s->hu);
+    double tp = s->tn - s->hu - tfuzz;
+    double tn1 = s->tn + tfuzz;
+    if ((t - tp) * (t - tn1) > 0.0) return -2;
+    double sfrac = (t - s->tn) / s->h;
+    double *yl = YH(s->l);
+    for (int i = 0; i < n; i++) dky[i] = yl[i];
+    for (int jb = 1; jb <= s->nq; jb++) {
+        int j = s->nq - jb;
+        double *yj = YH(j + 1);
+        for (int i = 0; i < n; i++) dky[i] = yj[i] + sfrac * dky[i];
+    }
+    return 0;
+}
+
+/* Driver DVODE dvode.f90:5654, ISTATE=1 / ITASK=1 path only. Returns ISTATE. */
+int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double tout, double rtol,
+               const double *atol, int mxstep)
+{
+    int n = s->n;
+    s->f = f;
+    s->ctx = ctx;
+    s->rtol = rtol;
+    s->atol = atol;
+    if (fabs(tout - *t) <= 0.0) return 1; /* :5995-5999: returns with ISTATE unchanged */
+    for (int i = 0; i < n; i++)
+        if (atol[i] < 0.0) return -3;
+    if (rtol < 0.0) return -3;
+    s->uround = DBL_EPSILON;
+    s->tn = *t;
+    s->jstart = 0;
+    s->ccmxj = 0.2;
+    s->msbj = 50;
+    s->nst = s->nje = s->nni = s->ncfn = s->netf = s->nlu = 0;
+    s->nslj = 0;
+    s->hu = 0.0;
+    s->nqu = 0;
+    s->hmin = 0.0;
+    s->hmxi = 0.0;
+    s->newh = 0;
+    s->newq = 1;
+    s->icf = 0;
+    s->ipup = 0;
+    s->nslp = 0;
+    s->crate = 1.0;
+    s->eta = 1.0;
+    int nslast = 0;
+    double *lf0 = YH(2);
+    f(ctx, *t, y, lf0);
+    s->nfe = 1;
+    memcpy(YH(1), y, n * sizeof(double));
+    s->nq = 1;
+    s->l = 2;
+    s->h = 1.0;
+    if (ewset(s, YH(1)) != 0) return -3;
+    double h0 = 0.0;
+    int niter = 0;
+    if (vhin(s, *t, YH(1), lf0, tout, &h0, &niter) != 0) return -3;
+    s->nfe += niter;
+    s->h = h0;
+    for (int i = 0; i < n; i++) lf0[i] *= h0;
+    int first = 1;
+    for (;;) {
+        if (!first) {
+            /* label 200 */
+            if (s->nst - nslast >= mxstep) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -1; }
+            if (ewset(s, YH(1)) != 0) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -6; }
+        }
+        first = 0;
+        /* label 210 */
+        double tolsf = s->uround * vnorm(n, YH(1), s->ewt);
+        if (tolsf > 1.0) {
+            if (s->nst == 0) return -3;
+            memcpy(y, YH(1), n * sizeof(double));
+            *t = s->tn;
+            return -2;
+        }
+        vstep(s);
+        if (s->kflag == -1) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -4; }
+        if (s->kflag <= -2) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -5; }
+        /* label 240/250/260 */
+        if ((s->tn - tout) * s->h < 0.0) continue;
+        vindy(s, tout, y);
+        *t = tout;
+        return 2;
+    }
+}

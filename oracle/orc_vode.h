@@ -1,0 +1,29 @@
+/* ORACLE (test infrastructure): DVODE MF=22 restatement, see orc_vode.c */
+#ifndef ORC_VODE_H
+#define ORC_VODE_H
+
+typedef void (*vode_rhs)(void *ctx, double t, const double *y, double *ydot);
+
+typedef struct {
+    int n;
+    double *yh, *ewt, *savf, *acor, *y, *ftem, *wm, *jsv;
+    int *ipvt;
+    double tau[14], el[14], tq[6];
+    double h, hu, hscal, hnew, tn, rc, prl1, rl1, eta, etamax, crate, drc, acnrm, conp, uround,
+        ccmxj, hmxi, hmin, rtol;
+    const double *atol;
+    int nq, l, lmax, nqwait, newq, newh, jstart, kflag, jcur, icf, ipup, nslp, nslj, msbj, nqu;
+    long nst, nfe, nje, nlu, nni, ncfn, netf;
+    vode_rhs f;
+    void *ctx;
+} vode_t;
+
+vode_t *vode_alloc(int n);
+void vode_free(vode_t *s);
+/* Integrate from *t to tout with a cold start (ISTATE=1, ITASK=1). Returns DVODE's ISTATE:
+ * 2 success, 1 tout==t, -1 mxstep, -2 too much accuracy, -3 illegal input, -4 error-test
+ * failures, -5 convergence failures, -6 EWT<=0.  On failure y,t hold the last good step. */
+int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double tout, double rtol,
+               const double *atol, int mxstep);
+
+#endif
