@@ -14,6 +14,7 @@
 #include "orc_vode.h"
 
 #include <float.h>
+#include <stdio.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -54,12 +55,14 @@ vode_t *vode_alloc(int n)
     s->wm = (double *)calloc((size_t)n * n, sizeof(double));
     s->jsv = (double *)calloc((size_t)n * n, sizeof(double));
     s->ipvt = (int *)calloc(n, sizeof(int));
+    s->trace = getenv("ORC_TRACE") ? fopen(getenv("ORC_TRACE"), "w") : NULL;
     return s;
 }
 
 void vode_free(vode_t *s)
 {
     if (!s) return;
+    if (s->trace) fclose((FILE *)s->trace);
     free(s->yh); free(s->ewt); free(s->savf); free(s->acor); free(s->y);
     free(s->ftem); free(s->wm); free(s->jsv); free(s->ipvt); free(s);
 }
@@ -382,6 +385,9 @@ static int vnls(vode_t *s, int *nflag)
             for (int i = 0; i < n; i++) y[i] = yh1[i] + acor[i];
             if (m != 0) s->crate = fmax(CRDOWN * s->crate, del / delp);
             double dcon = del * fmin(1.0, s->crate) / s->tq[4];
+            if (s->trace)
+                fprintf((FILE *)s->trace, "%.17g %.17g %d %d %.6e %.6e %.6e %ld.%d\n", s->tn, s->h, s->nq, m, del, dcon, s->rc,
+                        s->nst, s->jcur);
             if (dcon <= 1.0) { /* label 80 */
                 *nflag = 0;
                 s->jcur = 0;

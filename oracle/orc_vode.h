@@ -16,6 +16,7 @@ typedef struct {
     long nst, nfe, nje, nlu, nni, ncfn, netf;
     vode_rhs f;
     void *ctx;
+    void *trace; /* FILE* when ORC_TRACE is set (debug) */
 } vode_t;
 
 vode_t *vode_alloc(int n);

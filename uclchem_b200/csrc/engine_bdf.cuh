@@ -1,0 +1,691 @@
+// engine_bdf.cuh -- batched variable-order, variable-step BDF (one cell per CTA).
+//
+// The step/order controller, error test, Nordsieck bookkeeping and chord-Newton
+// logic are those of DVODE (dvode.f90: DVODE :5654, DVHIN :6768, DVINDY :6901,
+// DVSTEP :7180, DVSET :7616, DVJUST :7790, DVNLSD :7926; constants :1875-1911)
+// with the same tolerances and WRMS norm.  Documented deviations from MF=22:
+//   * the Jacobian is analytic (DVODE: finite differences); it is saved and reused
+//     exactly as DVODE's JSV=1 policy prescribes (dvode.f90:8200-8206);
+//   * P is factorised with a fixed-pattern sparse LU without pivoting.
+// Scalar control runs on thread 0 between barriers; vector work is one thread per
+// equation; RHS / Jacobian / LU / solves are the block-parallel programs of
+// engine_core.cuh.
+#pragma once
+#include "engine_la.cuh"
+
+#define V_ADDON 1.0e-6
+#define V_BIAS1 6.0
+#define V_BIAS2 6.0
+#define V_BIAS3 10.0
+#define V_CCMAX 0.3
+#define V_CORTES 0.1
+#define V_CRDOWN 0.3
+#define V_ETACF 0.25
+#define V_ETAMIN 0.1
+#define V_ETAMX1 1.0e4
+#define V_ETAMX2 10.0
+#define V_ETAMX3 10.0
+#define V_ETAMXF 0.2
+#define V_RDIV 2.0
+#define V_THRESH 1.5
+#define V_KFC (-3)
+#define V_KFH (-15)
+#define V_MAXCOR 3
+#define V_MSBP 20
+#define V_MSBJ 50
+#define V_CCMXJ 0.2
+#define V_MXNCF 10
+#define V_MAXORD 5
+
+#define T0_BEGIN BLOCK_SYNC(); if (threadIdx.x == 0) {
+#define T0_END } BLOCK_SYNC();
+
+// DVSET dvode.f90:7616 (BDF branch :7739-7786); thread 0 only. 1-based arrays.
+__device__ __noinline__ void vset_dev(Scalars &st)
+{
+    double *el = st.el, *tq = st.tq, *tau = st.tau;
+    const int nq = st.nq, l = st.l;
+    const double flotl = (double)l;
+    const int nqm1 = nq - 1, nqm2 = nq - 2;
+    for (int i = 3; i <= l; i++) el[i] = 0.0;
+    el[1] = 1.0;
+    el[2] = 1.0;
+    double alph0 = -1.0, ahatn0 = -1.0, hsum = st.h, rxi = 1.0, rxis = 1.0;
+    if (nq != 1) {
+        for (int j = 1; j <= nqm2; j++) {
+            hsum += tau[j];
+            rxi = st.h / hsum;
+            int jp1 = j + 1;
+            alph0 -= 1.0 / (double)jp1;
+            for (int iback = 1; iback <= jp1; iback++) {
+                int i = (j + 3) - iback;
+                el[i] = el[i] + el[i - 1] * rxi;
+            }
+        }
+        alph0 -= 1.0 / (double)nq;
+        rxis = -el[2] - alph0;
+        hsum += tau[nqm1];
+        rxi = st.h / hsum;
+        ahatn0 = -el[2] - rxi;
+        for (int iback = 1; iback <= nq; iback++) {
+            int i = (nq + 2) - iback;
+            el[i] = el[i] + el[i - 1] * rxis;
+        }
+    }
+    double t1 = 1.0 - ahatn0 + alph0;
+    double t2 = 1.0 + (double)nq * t1;
+    tq[2] = fabs(alph0 * t2 / t1);
+    tq[5] = fabs(t2 / (el[l] * rxi / rxis));
+    if (st.nqwait == 1) {
+        double cnqm1 = rxis / el[l];
+        double t3 = alph0 + 1.0 / (double)nq;
+        double t4 = ahatn0 + rxi;
+        double elp = t3 / (1.0 - t4 + t3);
+        tq[1] = fabs(elp / cnqm1);
+        hsum += tau[nq];
+        rxi = st.h / hsum;
+        double t5 = alph0 - 1.0 / (double)(nq + 1);
+        double t6 = ahatn0 - rxi;
+        elp = t2 / (1.0 - t6 + t5);
+        tq[3] = fabs(elp * rxi * (flotl + 1.0) * t5);
+    }
+    tq[4] = V_CORTES * tq[2];
+}
+
+// DVJUST dvode.f90:7790 (BDF :7862-7921).  Ends with a barrier.
+__device__ __noinline__ void vjust_dev(Smem &s, int iord)
+{
+    Scalars &st = s.st;
+    const int tid = threadIdx.x;
+    const int nq = st.nq, l = st.l, lmax = st.lmax;
+    if (nq == 2 && iord != 1) return; // block-uniform
+    BLOCK_SYNC();
+    if (tid == 0) {
+        double *el = st.el, *tau = st.tau;
+        for (int i = 1; i <= lmax; i++) el[i] = 0.0;
+        el[3] = 1.0;
+        if (iord != 1) {
+            double hsum = 0.0;
+            for (int j = 1; j <= nq - 2; j++) {
+                hsum += tau[j];
+                double xi = hsum / st.hscal;
+                int jp1 = j + 1;
+                for (int iback = 1; iback <= jp1; iback++) {
+                    int i = (j + 4) - iback;
+                    el[i] = el[i] * xi + el[i - 1];
+                }
+            }
+        } else {
+            double alph0 = -1.0, alph1 = 1.0, prod = 1.0, xiold = 1.0, hsum = st.hscal;
+            if (nq != 1) {
+                for (int j = 1; j <= nq - 1; j++) {
+                    int jp1 = j + 1;
+                    hsum += tau[jp1];
+                    double xi = hsum / st.hscal;
+                    prod *= xi;
+                    alph0 -= 1.0 / (double)jp1;
+                    alph1 += 1.0 / xi;
+                    for (int iback = 1; iback <= jp1; iback++) {
+                        int i = (j + 4) - iback;
+                        el[i] = el[i] * xiold + el[i - 1];
+                    }
+                    xiold = xi;
+                }
+            }
+            st.del = (-alph0 - alph1) / prod; // T1, parked in st.del for the vector part
+        }
+    }
+    BLOCK_SYNC();
+    if (tid < NEQ) {
+        if (iord != 1) {
+            double yl = s.yh[l - 1][tid];
+            for (int j = 3; j <= nq; j++) s.yh[j - 1][tid] -= yl * st.el[j];
+        } else {
+            double v = st.del * s.yh[lmax - 1][tid];
+            s.yh[l][tid] = v; // column LP1 = L+1
+            for (int j = 3; j <= nq + 1; j++) s.yh[j - 1][tid] += st.el[j] * v;
+        }
+    }
+    BLOCK_SYNC();
+}
+
+// Pascal-triangle predict / retract, dvode.f90:7367-7375 / :7396-7402 (per equation, no barrier)
+__device__ __forceinline__ void predict_dev(Smem &s, int nq, int sign)
+{
+    const int i = threadIdx.x;
+    if (i < NEQ) {
+        double c[LMAXORD];
+#pragma unroll
+        for (int j = 0; j < LMAXORD; j++) c[j] = s.yh[j][i];
+        for (int jb = 1; jb <= nq; jb++)
+            for (int j = nq - jb; j < nq; j++) {
+                // j runs over columns (0-based) I1..NQ-1 in increasing order
+                if (sign > 0) c[j] += c[j + 1]; else c[j] -= c[j + 1];
+            }
+#pragma unroll
+        for (int j = 0; j < LMAXORD; j++) s.yh[j][i] = c[j];
+    }
+}
+
+// DVNLSD dvode.f90:7926.  On return st.nflag = 0 (converged, st.acnrm set) or -1.
+__device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
+{
+    Scalars &st = s.st;
+    const int tid = threadIdx.x;
+    for (;;) { // label 10
+        if (tid < NEQ) s.y[tid] = s.yh[0][tid];
+        T0_BEGIN
+        st.m_iter = 0;
+        st.delp = 0.0;
+        st.nfe++;
+        T0_END
+        rhs_eval(s, s.savf);
+        if (st.ipup > 0) { // block-uniform (published before the last barrier)
+            // DVJAC dvode.f90:8200-8206: re-evaluate the Jacobian or reuse the saved copy
+            T0_BEGIN
+            int jok = 1;
+            if (st.nst_call == 0 || st.nst_call > st.nslj + V_MSBJ) jok = -1;
+            if (st.icf == 1 && st.drc < V_CCMXJ) jok = -1;
+            if (st.icf == 2) jok = -1;
+            st.flag2 = jok;
+            if (jok == -1) {
+                st.nje++;
+                st.nslj = st.nst_call;
+                st.jcur = 1;
+            } else {
+                st.jcur = 0;
+            }
+            st.nlu++;
+            T0_END
+            const bool fresh = st.flag2 == -1;
+            if (fresh) jac_eval(s);
+            form_p(s, st.h * st.rl1, b.jsv, fresh);
+            bool ok = factor_p(s, b);
+            T0_BEGIN
+            st.ipup = 0;
+            st.rc = 1.0;
+            st.drc = 0.0;
+            st.crate = 1.0;
+            st.nslp = st.nst_call;
+            st.flag = ok ? 0 : 1;
+            if (!ok) st.nsing++;
+            T0_END
+            if (st.flag) break; // singular: label 70
+        }
+        if (tid < NEQ) s.acor[tid] = 0.0;
+        int outcome; // 1 converged, 2 diverged
+        for (;;) {   // label 30/40
+            BLOCK_SYNC();
+            if (tid < NAUG) {
+                int o = net_perm[tid];
+                double v = 0.0;
+                if (o < NEQ && o != NET_IB && o != NET_IS)
+                    v = (st.rl1 * st.h) * s.savf[o] - (st.rl1 * s.yh[1][o] + s.acor[o]);
+                s.xs[tid] = v;
+            }
+            BLOCK_SYNC();
+            const bool dump = b.trace && b.dump && b.trace_n == b.dump_at;
+            if (dump) {
+                double *D = b.dump;
+                if (tid < NEQ) {
+                    D[tid] = s.y[tid]; D[NEQ + tid] = s.yh[0][tid]; D[2 * NEQ + tid] = s.yh[1][tid];
+                    D[3 * NEQ + tid] = s.acor[tid]; D[4 * NEQ + tid] = s.savf[tid]; D[6 * NEQ + tid] = s.ewt[tid];
+                }
+                if (tid == 0) {
+                    double *q = D + 7 * NEQ;
+                    q[0] = st.h; q[1] = st.rl1; q[2] = st.rc; q[3] = st.tn; q[4] = st.nq; q[5] = st.m_iter;
+                    q[6] = st.nst_call; q[7] = st.jcur; q[8] = st.tq[4]; q[9] = st.crate;
+                    for (int w = 0; w < 64; w++) D[7 * NEQ + 16 + 2 * NET_NVAL + NAUG + w] = st.dbg[w];
+                }
+                for (int i = tid; i < NET_NVAL; i += NT) { D[7 * NEQ + 16 + i] = b.jsv[i]; D[7 * NEQ + 16 + NET_NVAL + i] = s.val[i]; }
+                for (int i = tid; i < NAUG; i += NT) D[7 * NEQ + 16 + 2 * NET_NVAL + i] = s.xs[i];
+            }
+            lin_solve(s);
+            double d = 0.0;
+            if (tid < NEQ) {
+                d = s.xs[net_iperm[tid]];
+                if (dump) b.dump[5 * NEQ + tid] = d;
+                if (fabs(st.rc - 1.0) > 0.0) d *= 2.0 / (1.0 + st.rc);
+            }
+            double t = 0.0;
+            if (tid < NEQ) {
+                t = d * s.ewt[tid];
+                t = t * t;
+            }
+            double del = sqrt(block_sum(s, b, t) / (double)NEQ);
+            if (tid < NEQ) {
+                double a = s.acor[tid] + d;
+                s.acor[tid] = a;
+                s.y[tid] = s.yh[0][tid] + a;
+            }
+            T0_BEGIN
+            st.nni++;
+            st.del = del;
+            if (st.m_iter != 0) st.crate = fmax(V_CRDOWN * st.crate, del / st.delp);
+            double dcon = del * fmin(1.0, st.crate) / st.tq[4];
+            if (b.trace && b.trace_n < b.trace_cap) {
+                double *r = b.trace + 8 * (size_t)b.trace_n;
+                r[0] = st.tn; r[1] = st.h; r[2] = st.nq; r[3] = st.m_iter; r[4] = del; r[5] = dcon; r[6] = st.rc;
+                r[7] = (double)st.nst_call + 1e-3 * st.jcur;
+            }
+            if (dcon <= 1.0) {
+                st.flag = 1;
+            } else {
+                st.m_iter++;
+                if (st.m_iter == V_MAXCOR || (st.m_iter >= 2 && del > V_RDIV * st.delp) || !isfinite(del)) {
+                    st.flag = 2;
+                    if (st.m_iter == V_MAXCOR) st.nmaxcor++; else st.ndiverge++;
+                } else {
+                    st.delp = del;
+                    st.flag = 0;
+                    st.nfe++;
+                }
+            }
+            T0_END
+            outcome = st.flag;
+            if (b.trace) b.trace_n++;
+            if (outcome != 0) break;
+            rhs_eval(s, s.savf);
+        }
+        if (outcome == 1) {
+            double acn = st.del;
+            if (st.m_iter > 0) acn = wrms_norm(s, b, s.acor, s.ewt);
+            T0_BEGIN
+            st.acnrm = acn;
+            st.nflag = 0;
+            st.jcur = 0;
+            st.icf = 0;
+            T0_END
+            return;
+        }
+        // label 60
+        if (st.jcur == 1) break;
+        T0_BEGIN
+        st.icf = 1;
+        st.ipup = 1;
+        T0_END
+    }
+    // label 70
+    T0_BEGIN
+    st.nflag = -1;
+    st.icf = 2;
+    st.ipup = 1;
+    T0_END
+}
+
+// DVSTEP dvode.f90:7180.  Result in st.kflag (0 ok, -1 error-test failures, -2 convergence failures).
+__device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
+{
+    Scalars &st = s.st;
+    const int tid = threadIdx.x;
+    int adj = 0;        // pending DVJUST (-1 / +1)
+    int do_rescale = 0; // label 60 pending
+    T0_BEGIN
+    st.told = st.tn;
+    st.ncf = 0;
+    st.nflag = 0;
+    st.kflag = 0;
+    st.jcur = 0;
+    st.flag = 0;
+    st.flag2 = 0;
+    if (st.jstart > 0) {
+        if (st.newh != 0) {
+            if (st.newq < st.nq) st.flag = -1;
+            else if (st.newq > st.nq) st.flag = 1;
+            st.flag2 = 1;
+        }
+    } else {
+        st.lmax = V_MAXORD + 1;
+        st.nq = 1;
+        st.l = 2;
+        st.tau[1] = st.h;
+        st.prl1 = 1.0;
+        st.rc = 0.0;
+        st.etamax = V_ETAMX1;
+        st.nqwait = 2;
+        st.hscal = st.h;
+    }
+    T0_END
+    adj = st.flag;
+    do_rescale = st.flag2;
+    if (adj != 0) {
+        vjust_dev(s, adj);
+        T0_BEGIN
+        st.nq = st.newq;
+        st.l = st.nq + 1;
+        st.nqwait = st.l;
+        T0_END
+    }
+    for (;;) {
+        // label 60 (rescale) + label 70 (advance, DVSET) scalar part
+        T0_BEGIN
+        if (do_rescale) {
+            st.h = st.hscal * st.eta;
+            st.hscal = st.h;
+            st.rc = st.rc * st.eta;
+        }
+        st.tn += st.h;
+        vset_dev(st);
+        st.rl1 = 1.0 / st.el[2];
+        st.rc = st.rc * (st.rl1 / st.prl1);
+        st.prl1 = st.rl1;
+        // head of DVNLSD
+        if (st.jstart == 0) st.nslp = 0;
+        if (st.nflag == 0) st.icf = 0;
+        if (st.nflag == -2) st.ipup = 1;
+        if (st.jstart == 0) st.ipup = 1;
+        st.drc = fabs(st.rc - 1.0);
+        if (st.drc > V_CCMAX || st.nst_call >= st.nslp + V_MSBP) st.ipup = 1;
+        T0_END
+        if (tid < NEQ) {
+            if (do_rescale) {
+                double r = 1.0;
+                for (int j = 2; j <= st.l; j++) {
+                    r *= st.eta;
+                    s.yh[j - 1][tid] *= r;
+                }
+            }
+        }
+        do_rescale = 0;
+        predict_dev(s, st.nq, +1);
+        vnls_dev(s, b);
+        if (st.nflag != 0) {
+            // corrector failed to converge: dvode.f90:7390-7408
+            predict_dev(s, st.nq, -1);
+            T0_BEGIN
+            st.ncf++;
+            st.ncfn++;
+            st.etamax = 1.0;
+            st.tn = st.told;
+            st.flag = 0;
+            if (st.ncf == V_MXNCF) {
+                st.kflag = -2;
+                st.flag = 1;
+            } else {
+                st.eta = V_ETACF;
+                st.nflag = -1;
+            }
+            T0_END
+            if (st.flag) break;
+            do_rescale = 1;
+            continue;
+        }
+        // label 80: local error test
+        T0_BEGIN
+        st.dsm = st.acnrm / st.tq[2];
+        st.flag = (st.dsm <= 1.0) ? 1 : 0;
+        T0_END
+        if (st.flag) {
+            // ---- successful step: dvode.f90:7417-7468 ----
+            if (tid < NEQ) {
+                double a = s.acor[tid];
+                for (int j = 1; j <= st.l; j++) s.yh[j - 1][tid] += st.el[j] * a;
+            }
+            T0_BEGIN
+            st.kflag = 0;
+            st.nst++;
+            st.nst_call++;
+            st.hu = st.h;
+            st.nqu = st.nq;
+            for (int iback = 1; iback <= st.nq; iback++) {
+                int i = st.l - iback;
+                st.tau[i + 1] = st.tau[i];
+            }
+            st.tau[1] = st.h;
+            st.nqwait--;
+            st.flag = (st.l != st.lmax && st.nqwait == 1) ? 1 : 0; // save ACOR for the order-up estimate
+            if (st.flag) st.conp = st.tq[5];
+            st.flag2 = (fabs(st.etamax - 1.0) > 0.0) ? 1 : 0;
+            T0_END
+            if (st.flag && tid < NEQ) s.yh[st.lmax - 1][tid] = s.acor[tid];
+            if (st.flag2) {
+                // label 130: step/order selection
+                double ddn = 0.0, dup = 0.0;
+                const bool full = (st.nqwait == 0); // block-uniform
+                if (full) {
+                    if (st.nq != 1) ddn = wrms_norm(s, b, s.yh[st.l - 1], s.ewt);
+                    if (st.l != st.lmax) {
+                        double cnquot = (st.tq[5] / st.conp) * pow(st.h / st.tau[2], (double)st.l);
+                        double t = 0.0;
+                        if (tid < NEQ) {
+                            double v = s.acor[tid] - cnquot * s.yh[st.lmax - 1][tid];
+                            s.savf[tid] = v;
+                            t = v * s.ewt[tid];
+                            t = t * t;
+                        }
+                        dup = sqrt(block_sum(s, b, t) / (double)NEQ);
+                    }
+                }
+                T0_BEGIN
+                double flotl = (double)st.l;
+                double etaq = 1.0 / (pow(V_BIAS2 * st.dsm, 1.0 / flotl) + V_ADDON);
+                int choose = 0;
+                st.flag = 0;
+                if (full) {
+                    st.nqwait = 2;
+                    double etaqm1 = 0.0, etaqp1 = 0.0;
+                    if (st.nq != 1) etaqm1 = 1.0 / (pow(V_BIAS1 * (ddn / st.tq[1]), 1.0 / (flotl - 1.0)) + V_ADDON);
+                    if (st.l != st.lmax) etaqp1 = 1.0 / (pow(V_BIAS3 * (dup / st.tq[3]), 1.0 / (flotl + 1.0)) + V_ADDON);
+                    if (etaq >= etaqp1) choose = (etaq < etaqm1) ? -1 : 0;
+                    else choose = (etaqp1 > etaqm1) ? 1 : -1;
+                    if (choose == -1) { st.eta = etaqm1; st.newq = st.nq - 1; }
+                    if (choose == 1) { st.eta = etaqp1; st.newq = st.nq + 1; st.flag = 1; }
+                }
+                if (choose == 0) { st.eta = etaq; st.newq = st.nq; }
+                if (st.eta < V_THRESH || fabs(st.etamax - 1.0) <= 0.0) {
+                    st.newq = st.nq;
+                    st.newh = 0;
+                    st.eta = 1.0;
+                    st.hnew = st.h;
+                } else {
+                    st.eta = fmin(st.eta, st.etamax);
+                    st.newh = 1;
+                    st.hnew = st.h * st.eta;
+                }
+                T0_END
+                if (st.flag && tid < NEQ) s.yh[st.lmax - 1][tid] = s.acor[tid];
+            } else {
+                T0_BEGIN
+                if (st.nqwait < 2) st.nqwait = 2;
+                st.newq = st.nq;
+                st.newh = 0;
+                st.eta = 1.0;
+                st.hnew = st.h;
+                T0_END
+            }
+            // label 250
+            if (tid < NEQ) s.acor[tid] *= 1.0 / st.tq[2];
+            T0_BEGIN
+            st.etamax = V_ETAMX3;
+            if (st.nst_call <= 10) st.etamax = V_ETAMX2;
+            T0_END
+            break;
+        }
+        // ---- label 100: error test failed ----
+        predict_dev(s, st.nq, -1);
+        T0_BEGIN
+        st.kflag--;
+        st.netf++;
+        st.nflag = -2;
+        st.tn = st.told;
+        st.etamax = 1.0;
+        st.flag = 0; // 0 retry with rescale, 1 give up, 2 order drop, 3 order-1 restart
+        if (st.kflag > V_KFC) {
+            double flotl = (double)st.l;
+            st.eta = 1.0 / (pow(V_BIAS2 * st.dsm, 1.0 / flotl) + V_ADDON);
+            st.eta = fmax(st.eta, V_ETAMIN);
+            if (st.kflag <= -2 && st.eta > V_ETAMXF) st.eta = V_ETAMXF;
+        } else if (st.kflag == V_KFH) {
+            st.kflag = -1;
+            st.flag = 1;
+        } else if (st.nq != 1) {
+            st.eta = V_ETAMIN;
+            st.flag = 2;
+        } else {
+            st.eta = V_ETAMIN;
+            st.h = st.h * st.eta;
+            st.hscal = st.h;
+            st.tau[1] = st.h;
+            st.nfe++;
+            st.nqwait = 10;
+            st.flag = 3;
+        }
+        T0_END
+        int f = st.flag;
+        if (f == 1) break;
+        if (f == 0) { do_rescale = 1; continue; }
+        if (f == 2) {
+            vjust_dev(s, -1);
+            T0_BEGIN
+            st.l = st.nq;
+            st.nq = st.nq - 1;
+            st.nqwait = st.l;
+            T0_END
+            do_rescale = 1;
+            continue;
+        }
+        // f == 3 (label 120): reload YH(:,2) = H*F(TN, Y) at the last corrector iterate
+        rhs_eval(s, s.savf);
+        if (tid < NEQ) s.yh[1][tid] = st.h * s.savf[tid];
+        do_rescale = 0;
+    }
+    T0_BEGIN
+    st.jstart = 1;
+    T0_END
+}
+
+// One DVODE call (ISTATE=1, ITASK=1): integrate s.abund from st.current_time to tout.
+// Returns DVODE's ISTATE; s.abund / st.current_time are updated as DVODE updates Y / T.
+__device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout)
+{
+    Scalars &st = s.st;
+    const int tid = threadIdx.x;
+    const double t0 = st.current_time;
+    if (fabs(tout - t0) <= 0.0) return 1;
+    const double uround = DBL_EPSILON;
+    T0_BEGIN
+    st.tn = t0;
+    st.jstart = 0;
+    st.nst_call = 0;
+    st.hu = 0.0;
+    st.nqu = 0;
+    st.newh = 0;
+    st.newq = 1;
+    st.icf = 0;
+    st.ipup = 0;
+    st.nslp = 0;
+    st.nslj = 0;
+    st.crate = 1.0;
+    st.eta = 1.0;
+    st.nq = 1;
+    st.l = 2;
+    st.nfe++;
+    T0_END
+    if (tid < NEQ) {
+        s.y[tid] = s.abund[tid];
+        s.yh[0][tid] = s.abund[tid];
+    }
+    BLOCK_SYNC();
+    rhs_eval(s, s.yh[1]);
+    double bad = 0.0;
+    if (tid < NEQ) {
+        double e = st.rtol * fabs(s.yh[0][tid]) + s.atol[tid];
+        if (e <= 0.0) bad = 1.0;
+        s.ewt[tid] = 1.0 / e;
+    }
+    if (block_sum(s, b, bad) > 0.0) return -3;
+    // ---- DVHIN dvode.f90:6768 ----
+    double h0;
+    {
+        const double tdist = fabs(tout - t0);
+        const double tround = uround * fmax(fabs(t0), fabs(tout));
+        if (tdist < 2.0 * tround) return -3;
+        const double hlb = 100.0 * tround;
+        double hub = 0.1 * tdist;
+        double cand = hub;
+        if (tid < NEQ) {
+            double delyi = 0.1 * fabs(s.yh[0][tid]) + s.atol[tid];
+            double afi = fabs(s.yh[1][tid]);
+            if (afi * hub > delyi) cand = delyi / afi;
+        }
+        hub = block_min(s, b, cand);
+        double hg = sqrt(hlb * hub);
+        double hnew = hg;
+        int iter = 0;
+        if (hub < hlb) {
+            h0 = copysign(hg, tout - t0);
+        } else {
+            for (;;) {
+                double h = copysign(hg, tout - t0);
+                if (tid < NEQ) s.y[tid] = s.yh[0][tid] + h * s.yh[1][tid];
+                BLOCK_SYNC();
+                rhs_eval(s, s.acor);
+                double t = 0.0;
+                if (tid < NEQ) {
+                    t = (s.acor[tid] - s.yh[1][tid]) / h * s.ewt[tid];
+                    t = t * t;
+                }
+                double yddnrm = sqrt(block_sum(s, b, t) / (double)NEQ);
+                if (yddnrm * hub * hub > 2.0) hnew = sqrt(2.0 / yddnrm);
+                else hnew = sqrt(hg * hub);
+                iter++;
+                if (iter >= 4) break;
+                double hrat = hnew / hg;
+                if (hrat > 0.5 && hrat < 2.0) break;
+                if (iter >= 2 && hnew > 2.0 * hg) { hnew = hg; break; }
+                hg = hnew;
+            }
+            double h = hnew * 0.5;
+            if (h < hlb) h = hlb;
+            if (h > hub) h = hub;
+            h0 = copysign(h, tout - t0);
+        }
+        T0_BEGIN
+        st.nfe += iter;
+        st.h = h0;
+        T0_END
+    }
+    if (tid < NEQ) s.yh[1][tid] *= h0;
+    bool first = true;
+    int istate = 2;
+    for (;;) {
+        if (!first) {
+            if (st.nst_call >= st.mxstep) { istate = -1; break; }
+            double badw = 0.0;
+            if (tid < NEQ) {
+                double e = st.rtol * fabs(s.yh[0][tid]) + s.atol[tid];
+                if (e <= 0.0) badw = 1.0;
+                s.ewt[tid] = 1.0 / e;
+            }
+            if (block_sum(s, b, badw) > 0.0) { istate = -6; break; }
+        }
+        first = false;
+        double tolsf = uround * wrms_norm(s, b, s.yh[0], s.ewt);
+        if (tolsf > 1.0) {
+            if (st.nst_call == 0) return -3;
+            istate = -2;
+            break;
+        }
+        vstep_dev(s, b);
+        if (st.kflag == -1) { istate = -4; break; }
+        if (st.kflag <= -2) { istate = -5; break; }
+        if ((st.tn - tout) * st.h < 0.0) continue;
+        // DVINDY_CORE dvode.f90:6901 with K=0: interpolate the Nordsieck polynomial back to TOUT
+        if (tid < NEQ) {
+            double sfrac = (tout - st.tn) / st.h;
+            double v = s.yh[st.l - 1][tid];
+            for (int j = st.nq - 1; j >= 0; j--) v = s.yh[j][tid] + sfrac * v;
+            s.abund[tid] = v;
+        }
+        T0_BEGIN
+        st.current_time = tout;
+        T0_END
+        return 2;
+    }
+    // failure exits: Y = YH(:,1), T = TN (dvode.f90:6595-6597)
+    if (tid < NEQ) s.abund[tid] = s.yh[0][tid];
+    T0_BEGIN
+    st.current_time = st.tn;
+    T0_END
+    return istate;
+}

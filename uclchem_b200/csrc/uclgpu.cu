@@ -1,0 +1,483 @@
+// uclgpu.cu -- kernels and the C ABI (include/uclgpu.h) of the B200 UCLCHEM engine.
+//
+// One persistent CTA per SM; CTAs pull cells from a device-side work counter, so
+// the >100x spread in per-cell cost (SURVEY.md hard part ii) is absorbed without a
+// lock-step batch.  No host-side fallback exists: without a usable device every
+// computing entry point returns UCLGPU_ERR_NO_DEVICE.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "engine_model.cuh"
+
+static_assert(NT % 32 == 0 && NT / 4 >= MDENSE, "dense mat-vec uses 4 lanes per row");
+static_assert(NT >= NAUG && NT >= 2 * NSURF + 0 && NT >= 128 + NSURF, "one thread per equation");
+static_assert(sizeof(Smem) <= 227 * 1024, "cell working set must fit in one SM's shared memory");
+
+// -------------------------------------------------------------------------------------
+// kernels
+// -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1) k_integrate(RunArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ long long cell_sh;
+    Blk b;
+    b.phase = 0;
+    b.jsv = a.jsave + (size_t)blockIdx.x * JSV_STRIDE;
+    if (threadIdx.x == 0) s.y[NEQ + 0] = 1.0; // constant-one factor slot of the extended state
+    for (;;) {
+        BLOCK_SYNC();
+        if (threadIdx.x == 0) cell_sh = (long long)atomicAdd(a.counter, 1ULL);
+        BLOCK_SYNC();
+        long long cell = cell_sh;
+        if (cell >= a.ncell) break;
+        b.trace = (cell == 0) ? a.trace : nullptr;
+        b.trace_cap = a.trace_cap;
+        b.trace_n = 0;
+        b.dump = (cell == 0) ? a.dump : nullptr;
+        b.dump_at = a.dump_at;
+        run_cell(s, b, a, cell);
+    }
+}
+
+// mode 0: rates (get_rates, wrap.f90:446-514); 1: F at the given state;
+// mode 2: get_odes semantics (wrap.f90:516-547: integrate 1e-7 s, then F);
+// mode 3: Newton solve P x = b with P = I - gamma*J at the given state
+struct ProbeArgs {
+    int mode;
+    long long ncell;
+    const double *params, *y;
+    double *out;
+    double gamma;
+    const double *rhs;
+    double *jsave;
+};
+
+__global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem &s = *reinterpret_cast<Smem *>(smem_raw);
+    Scalars &st = s.st;
+    Blk b;
+    b.phase = 0;
+    b.jsv = a.jsave + (size_t)blockIdx.x * JSV_STRIDE;
+    b.trace = nullptr;
+    b.dump = nullptr;
+    b.trace_cap = b.trace_n = b.dump_at = 0;
+    const int tid = threadIdx.x;
+    if (tid == 0) s.y[NEQ + 0] = 1.0;
+    for (long long cell = blockIdx.x; cell < a.ncell; cell += gridDim.x) {
+        BLOCK_SYNC();
+        if (tid < UCLGPU_NPARAM) st.p[tid] = a.params[(size_t)tid * a.ncell + cell];
+        for (int i = tid; i < NREAC; i += NT) s.rate[i] = 0.0;
+        T0_BEGIN
+        st.kind = UCLGPU_CLOUD;
+        st.current_time = 0.0;
+        st.phi = st.p[UCL_P_PHI];
+        st.abstol_factor = st.p[UCL_P_ABSTOL_FACTOR];
+        st.mxstep = (int)st.p[UCL_P_MXSTEP];
+        st.rtol = st.p[UCL_P_RELTOL];
+        st.last_temp = 99.0e99;
+        st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;
+        st.nsing = st.nmaxcor = st.ndiverge = st.nfailcall = 0;
+        st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = st.cyc_total = 0;
+        initialize_physics_dev(st);
+        T0_END
+        if (tid < NSPEC) s.abund[tid] = a.y[(size_t)cell * NEQ + tid];
+        if (tid == NSPEC) s.abund[tid] = st.p[UCL_P_INITIALDENS];
+        BLOCK_SYNC();
+        if (a.mode == 2) {
+            T0_BEGIN
+            st.target_time = 1.0e-7;
+            T0_END
+            update_chemistry_dev(s, b);
+        }
+        chemistry_setup_dev(s);
+        if (a.mode == 0) {
+            for (int i = tid; i < NREAC; i += NT) a.out[(size_t)cell * NREAC + i] = s.rate[i];
+            continue;
+        }
+        if (tid < NEQ) s.y[tid] = s.abund[tid];
+        BLOCK_SYNC();
+        rhs_eval(s, s.savf);
+        if (a.mode == 1 || a.mode == 2) {
+            for (int i = tid; i < NEQ; i += NT) a.out[(size_t)cell * NEQ + i] = s.savf[i];
+            continue;
+        }
+        jac_eval(s);
+        form_p(s, a.gamma, b.jsv, true);
+        bool ok = factor_p(s, b);
+        if (tid < NAUG) {
+            int o = net_perm[tid];
+            s.xs[tid] = (o < NEQ && o != NET_IB && o != NET_IS) ? a.rhs[(size_t)cell * NEQ + o] : 0.0;
+        }
+        BLOCK_SYNC();
+        lin_solve(s);
+        for (int i = tid; i < NAUG; i += NT) a.out[(size_t)cell * NAUG + i] = ok ? s.xs[net_iperm[i]] : nan("");
+    }
+}
+
+// -------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------
+struct Device {
+    int id = -1;
+    int sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned long long *counter = nullptr;
+    double *jsave = nullptr;
+    double last_ms = 0.0;
+    long long last_launches = 0;
+};
+static std::vector<Device> g_dev;
+static bool g_init = false;
+static char g_err[256] = "";
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            snprintf(g_err, sizeof(g_err), "%s at %s:%d", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return UCLGPU_ERR_CUDA;                                                           \
+        }                                                                                     \
+    } while (0)
+
+extern "C" int uclgpu_init(int ndev, const int *devs)
+{
+    if (g_init) return 0;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device visible");
+        return UCLGPU_ERR_NO_DEVICE;
+    }
+    std::vector<int> ids;
+    if (ndev <= 0 || !devs) for (int i = 0; i < count; i++) ids.push_back(i);
+    else for (int i = 0; i < ndev; i++) ids.push_back(devs[i]);
+    for (int id : ids) {
+        if (id < 0 || id >= count) return UCLGPU_ERR_BAD_ARGUMENT;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) {
+            snprintf(g_err, sizeof(g_err), "device %d is sm_%d%d; this library is built for sm_100a only", id,
+                     prop.major, prop.minor);
+            return UCLGPU_ERR_NO_DEVICE;
+        }
+        Device d;
+        d.id = id;
+        d.sms = prop.multiProcessorCount;
+        CK(cudaSetDevice(id));
+        CK(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&d.ev0));
+        CK(cudaEventCreate(&d.ev1));
+        CK(cudaMalloc(&d.counter, sizeof(unsigned long long)));
+        CK(cudaMalloc(&d.jsave, sizeof(double) * JSV_STRIDE * (size_t)d.sms));
+        CK(cudaFuncSetAttribute(k_integrate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+        g_dev.push_back(d);
+    }
+    g_init = true;
+    return 0;
+}
+
+extern "C" void uclgpu_shutdown(void)
+{
+    for (auto &d : g_dev) {
+        cudaSetDevice(d.id);
+        cudaFree(d.counter);
+        cudaFree(d.jsave);
+        cudaEventDestroy(d.ev0);
+        cudaEventDestroy(d.ev1);
+        cudaStreamDestroy(d.stream);
+    }
+    g_dev.clear();
+    g_init = false;
+}
+
+extern "C" const char *uclgpu_strerror(int code)
+{
+    switch (code) {
+    case 0: return "success";
+    case UCLGPU_PARAMETER_READ_ERROR: return "Parameter read failed. Likely due to a mispelled parameter name, compare your dictionary to the parameters docs.";
+    case UCLGPU_PHYSICS_INIT_ERROR: return "Physics intiialization failed. Often due to user chosing unacceptable parameters such as hot core masses or shock velocities that are not in the parameterised range.";
+    case UCLGPU_CHEM_INIT_ERROR: return "Chemistry initialization failed";
+    case UCLGPU_INT_UNRECOVERABLE_ERROR: return "Unrecoverable integrator error, DVODE failed to integrate the ODEs in a way that UCLCHEM could not fix. Run UCLCHEM tests to check your network works at all then try to see if bad parameter combination is at play.";
+    case UCLGPU_INT_TOO_MANY_FAILS_ERROR: return "Too many integrator fails. DVODE failed to integrate the ODE and UCLCHEM repeatedly altered settings to try to make it pass but tried too many times without success so code aborted to stop infinite loop.";
+    case UCLGPU_NOT_ENOUGH_TIMEPOINTS_ERROR: return "Not enough time points allocated in the time array. Increase the number of time points in the time array and try again.";
+    case UCLGPU_ERR_NO_DEVICE: return g_err[0] ? g_err : "no usable sm_100 CUDA device (this library has no CPU fallback)";
+    case UCLGPU_ERR_BAD_ARGUMENT: return "bad argument";
+    case UCLGPU_ERR_CUDA: return g_err[0] ? g_err : "CUDA error";
+    case UCLGPU_ERR_NOT_INITIALISED: return "uclgpu_init has not been called";
+    }
+    return "unknown error code";
+}
+
+extern "C" int uclgpu_nspec(void) { return NSPEC; }
+extern "C" int uclgpu_nreac(void) { return NREAC; }
+extern "C" int uclgpu_naug(void) { return NAUG; }
+extern "C" const char *uclgpu_species_name(int i) { return (i >= 0 && i < NSPEC) ? net_species_names[i] : ""; }
+extern "C" const char *uclgpu_network_tag(void) { return NET_TAG; }
+
+extern "C" int uclgpu_default_params(int64_t ncell, double *params)
+{
+    // defaultparameters.f90:18-122; REAL(dp) :: x = <default-real literal> keeps float32 rounding
+    if (ncell < 0 || !params) return UCLGPU_ERR_BAD_ARGUMENT;
+    double d[UCLGPU_NPARAM];
+    for (int k = 0; k < UCLGPU_NPARAM; k++) d[k] = 0.0;
+    d[UCL_P_INITIALTEMP] = 10.0; d[UCL_P_INITIALDENS] = 1.00e2; d[UCL_P_FINALDENS] = 1.00e5;
+    d[UCL_P_FINALTIME] = 5.0e6; d[UCL_P_RADFIELD] = 1.0; d[UCL_P_ZETA] = 1.0; d[UCL_P_ROUT] = (double)0.05f;
+    d[UCL_P_BASEAV] = 2.0; d[UCL_P_POINTS] = 1; d[UCL_P_BM0] = 1.0; d[UCL_P_FREEZEFACTOR] = 1.0;
+    d[UCL_P_FREEFALLFACTOR] = 1.0; d[UCL_P_DESORB] = 1; d[UCL_P_H2DESORB] = 1; d[UCL_P_CRDESORB] = 1;
+    d[UCL_P_UVDESORB] = 1; d[UCL_P_THERMDESORB] = 1; d[UCL_P_METALLICITY] = 1.0; d[UCL_P_ION] = 2;
+    d[UCL_P_FH] = 0.5; d[UCL_P_FHE] = (double)0.1f; d[UCL_P_FC] = 1.77e-04; d[UCL_P_FO] = 3.34e-04;
+    d[UCL_P_FN] = 6.18e-05; d[UCL_P_FS] = 3.51e-6; d[UCL_P_FMG] = 2.256e-06; d[UCL_P_FSI] = 1.78e-06;
+    d[UCL_P_FCL] = 3.39e-08; d[UCL_P_FP] = 7.78e-08; d[UCL_P_FFE] = 2.01e-7; d[UCL_P_FF] = 3.6e-08;
+    d[UCL_P_RELTOL] = 1e-8; d[UCL_P_ABSTOL_FACTOR] = 1.0e-14; d[UCL_P_ABSTOL_MIN] = 1.0e-25;
+    d[UCL_P_MXSTEP] = 10000; d[UCL_P_EBMAXH2] = 1.21e3; d[UCL_P_EBMAXCR] = 1.21e3; d[UCL_P_EBMAXUVCR] = 1.0e4;
+    d[UCL_P_EPSILON] = (double)0.01f; d[UCL_P_UV_YIELD] = (double)0.03f; d[UCL_P_PHI] = 1.0e5;
+    d[UCL_P_UVCREFF] = 1.0e-3; d[UCL_P_OMEGA] = 0.5; d[UCL_P_TEMPINDX] = 1; d[UCL_P_MAXTEMP] = 300.0;
+    d[UCL_P_TIMESTEPFACTOR] = 0.01;
+    for (int k = 0; k < UCLGPU_NPARAM; k++)
+        for (int64_t c = 0; c < ncell; c++) params[(size_t)k * ncell + c] = d[k];
+    return 0;
+}
+
+static int grid_blocks(const Device &d, long long ncell)
+{
+    long long g = d.sms; // one CTA per SM (the cell's working set fills the SM's shared memory)
+    if (ncell < g) g = ncell;
+    return (int)(g < 1 ? 1 : g);
+}
+
+static int launch_integrate(Device &d, const RunArgs &a)
+{
+    CK(cudaSetDevice(d.id));
+    CK(cudaMemsetAsync(d.counter, 0, sizeof(unsigned long long), d.stream));
+    RunArgs aa = a;
+    aa.counter = d.counter;
+    aa.jsave = d.jsave;
+    // debug: UCLGPU_TRACE=<records> UCLGPU_TRACE_FILE=<path> dumps cell 0's Newton iterations
+    double *d_trace = nullptr;
+    const char *tr = getenv("UCLGPU_TRACE");
+    int cap = tr ? atoi(tr) : 0;
+    if (cap > 0) {
+        CK(cudaMalloc(&d_trace, sizeof(double) * 8 * (size_t)cap));
+        CK(cudaMemsetAsync(d_trace, 0, sizeof(double) * 8 * (size_t)cap, d.stream));
+        aa.trace = d_trace;
+        aa.trace_cap = cap;
+    }
+    double *d_dump = nullptr;
+    const size_t dump_n = 7 * NEQ + 16 + 2 * (size_t)NET_NVAL + NAUG + 64;
+    if (cap > 0 && getenv("UCLGPU_DUMP_AT")) {
+        CK(cudaMalloc(&d_dump, sizeof(double) * dump_n));
+        CK(cudaMemsetAsync(d_dump, 0, sizeof(double) * dump_n, d.stream));
+        aa.dump = d_dump;
+        aa.dump_at = atoi(getenv("UCLGPU_DUMP_AT"));
+    }
+    CK(cudaEventRecord(d.ev0, d.stream));
+    k_integrate<<<grid_blocks(d, a.ncell), NT, sizeof(Smem), d.stream>>>(aa);
+    CK(cudaEventRecord(d.ev1, d.stream));
+    CK(cudaGetLastError());
+    if (cap > 0) {
+        std::vector<double> h(8 * (size_t)cap);
+        CK(cudaMemcpyAsync(h.data(), d_trace, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        const char *fn = getenv("UCLGPU_TRACE_FILE");
+        FILE *f = fopen(fn ? fn : "uclgpu_trace.bin", "wb");
+        if (f) { fwrite(h.data(), sizeof(double), h.size(), f); fclose(f); }
+        cudaFree(d_trace);
+        if (d_dump) {
+            std::vector<double> hd(dump_n);
+            CK(cudaMemcpy(hd.data(), d_dump, sizeof(double) * dump_n, cudaMemcpyDeviceToHost));
+            const char *fd = getenv("UCLGPU_DUMP_FILE");
+            FILE *g = fopen(fd ? fd : "uclgpu_dump.bin", "wb");
+            if (g) { fwrite(hd.data(), sizeof(double), hd.size(), g); fclose(g); }
+            cudaFree(d_dump);
+        }
+    }
+    d.last_launches = 1;
+    return 0;
+}
+
+extern "C" int uclgpu_run_grid_device(int dev, uclgpu_model_kind kind, int64_t ncell, const double *d_params,
+                                      const double *d_y0, double *d_y_final, double *d_phys_final,
+                                      int32_t *d_flag, uclgpu_stats *d_stats, void *cuda_stream)
+{
+    if (!g_init) return UCLGPU_ERR_NOT_INITIALISED;
+    Device *d = nullptr;
+    for (auto &x : g_dev) if (x.id == dev) d = &x;
+    if (!d || ncell < 0 || !d_params || !d_y_final || !d_flag) return UCLGPU_ERR_BAD_ARGUMENT;
+    if (ncell == 0) return 0;
+    (void)cuda_stream; // the library launches on its own stream and synchronises before returning
+    RunArgs a;
+    memset(&a, 0, sizeof(a));
+    a.kind = (int)kind; a.ncell = ncell; a.params = d_params; a.y0 = d_y0; a.y_final = d_y_final;
+    a.phys_final = d_phys_final; a.flag = d_flag; a.stats = d_stats;
+    int rc = launch_integrate(*d, a);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(d->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+    d->last_ms = ms;
+    return 0;
+}
+
+extern "C" int uclgpu_last_kernel_ms(int dev, double *ms, int64_t *launches)
+{
+    for (auto &x : g_dev)
+        if (x.id == dev) {
+            if (ms) *ms = x.last_ms;
+            if (launches) *launches = x.last_launches;
+            return 0;
+        }
+    return UCLGPU_ERR_BAD_ARGUMENT;
+}
+
+struct DevBuf {
+    double *params = nullptr, *y0 = nullptr, *y_final = nullptr, *phys = nullptr, *ptraj = nullptr, *ctraj = nullptr,
+           *rtraj = nullptr, *tdiss = nullptr;
+    int32_t *flag = nullptr;
+    uclgpu_stats *stats = nullptr;
+    void release()
+    {
+        cudaFree(params); cudaFree(y0); cudaFree(y_final); cudaFree(phys); cudaFree(ptraj); cudaFree(ctraj);
+        cudaFree(rtraj); cudaFree(tdiss); cudaFree(flag); cudaFree(stats);
+    }
+};
+
+extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const double *params, const double *y0,
+                               double *y_final, double *phys_final, int32_t *flag, uclgpu_stats *stats,
+                               const uclgpu_opts *opts)
+{
+    if (!g_init) {
+        int rc = uclgpu_init(0, nullptr);
+        if (rc) return rc;
+    }
+    if (ncell < 0 || !params || !y_final || !flag) return UCLGPU_ERR_BAD_ARGUMENT;
+    if ((int)kind < 0 || (int)kind > 2) return UCLGPU_ERR_BAD_ARGUMENT;
+    if (ncell == 0) return 0;
+    const int nd = (int)g_dev.size();
+    const int T1 = opts ? opts->timepoints + 1 : 0;
+    std::vector<DevBuf> bufs(nd);
+    std::vector<long long> lo(nd + 1);
+    for (int i = 0; i <= nd; i++) lo[i] = ncell * i / nd; // contiguous shards, no inter-GPU traffic
+    int rc = 0;
+    for (int i = 0; i < nd && !rc; i++) {
+        Device &d = g_dev[i];
+        DevBuf &B = bufs[i];
+        long long n = lo[i + 1] - lo[i];
+        if (n == 0) continue;
+        rc = [&]() -> int {
+            CK(cudaSetDevice(d.id));
+            CK(cudaMalloc(&B.params, sizeof(double) * UCLGPU_NPARAM * n));
+            CK(cudaMalloc(&B.y_final, sizeof(double) * NEQ * n));
+            CK(cudaMalloc(&B.phys, sizeof(double) * UCLGPU_NPHYS * n));
+            CK(cudaMalloc(&B.flag, sizeof(int32_t) * n));
+            CK(cudaMalloc(&B.stats, sizeof(uclgpu_stats) * n));
+            CK(cudaMemcpy2DAsync(B.params, sizeof(double) * n, params + lo[i], sizeof(double) * ncell,
+                                 sizeof(double) * n, UCLGPU_NPARAM, cudaMemcpyHostToDevice, d.stream));
+            if (y0) {
+                CK(cudaMalloc(&B.y0, sizeof(double) * NEQ * n));
+                CK(cudaMemcpyAsync(B.y0, y0 + (size_t)lo[i] * NEQ, sizeof(double) * NEQ * n, cudaMemcpyHostToDevice,
+                                   d.stream));
+            }
+            RunArgs a;
+            memset(&a, 0, sizeof(a));
+            a.kind = (int)kind; a.ncell = n; a.params = B.params; a.y0 = B.y0; a.y_final = B.y_final;
+            a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
+            if (opts) {
+                a.timepoints = opts->timepoints;
+                if (opts->physics_traj) { CK(cudaMalloc(&B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n)); CK(cudaMemsetAsync(B.ptraj, 0, sizeof(double) * UCLGPU_NPHYS * T1 * n, d.stream)); a.phys_traj = B.ptraj; }
+                if (opts->chem_traj) { CK(cudaMalloc(&B.ctraj, sizeof(double) * NSPEC * T1 * n)); CK(cudaMemsetAsync(B.ctraj, 0, sizeof(double) * NSPEC * T1 * n, d.stream)); a.chem_traj = B.ctraj; }
+                if (opts->rates_traj) { CK(cudaMalloc(&B.rtraj, sizeof(double) * NREAC * T1 * n)); CK(cudaMemsetAsync(B.rtraj, 0, sizeof(double) * NREAC * T1 * n, d.stream)); a.rates_traj = B.rtraj; }
+                if (opts->dissipation_time) { CK(cudaMalloc(&B.tdiss, sizeof(double) * n)); a.tdiss = B.tdiss; }
+            }
+            return launch_integrate(d, a);
+        }();
+    }
+    for (int i = 0; i < nd && !rc; i++) {
+        Device &d = g_dev[i];
+        DevBuf &B = bufs[i];
+        long long n = lo[i + 1] - lo[i];
+        if (n == 0) continue;
+        rc = [&]() -> int {
+            CK(cudaSetDevice(d.id));
+            CK(cudaMemcpyAsync(y_final + (size_t)lo[i] * NEQ, B.y_final, sizeof(double) * NEQ * n, cudaMemcpyDeviceToHost, d.stream));
+            if (phys_final) CK(cudaMemcpyAsync(phys_final + (size_t)lo[i] * UCLGPU_NPHYS, B.phys, sizeof(double) * UCLGPU_NPHYS * n, cudaMemcpyDeviceToHost, d.stream));
+            CK(cudaMemcpyAsync(flag + lo[i], B.flag, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+            if (stats) CK(cudaMemcpyAsync(stats + lo[i], B.stats, sizeof(uclgpu_stats) * n, cudaMemcpyDeviceToHost, d.stream));
+            if (opts) {
+                if (opts->physics_traj) CK(cudaMemcpyAsync(opts->physics_traj + (size_t)lo[i] * T1 * UCLGPU_NPHYS, B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n, cudaMemcpyDeviceToHost, d.stream));
+                if (opts->chem_traj) CK(cudaMemcpyAsync(opts->chem_traj + (size_t)lo[i] * T1 * NSPEC, B.ctraj, sizeof(double) * NSPEC * T1 * n, cudaMemcpyDeviceToHost, d.stream));
+                if (opts->rates_traj) CK(cudaMemcpyAsync(opts->rates_traj + (size_t)lo[i] * T1 * NREAC, B.rtraj, sizeof(double) * NREAC * T1 * n, cudaMemcpyDeviceToHost, d.stream));
+                if (opts->dissipation_time) CK(cudaMemcpyAsync(opts->dissipation_time + lo[i], B.tdiss, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+            }
+            CK(cudaStreamSynchronize(d.stream));
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+            d.last_ms = ms;
+            return 0;
+        }();
+    }
+    for (int i = 0; i < nd; i++) {
+        cudaSetDevice(g_dev[i].id);
+        if (rc) cudaStreamSynchronize(g_dev[i].stream);
+        bufs[i].release();
+    }
+    return rc;
+}
+
+static int run_probe(int mode, int64_t ncell, const double *params, const double *y, double *out, size_t out_per_cell,
+                     double gamma, const double *rhs)
+{
+    if (!g_init) {
+        int rc = uclgpu_init(0, nullptr);
+        if (rc) return rc;
+    }
+    if (ncell <= 0 || !params || !y || !out) return UCLGPU_ERR_BAD_ARGUMENT;
+    Device &d = g_dev[0];
+    CK(cudaSetDevice(d.id));
+    double *dp = nullptr, *dy = nullptr, *dout = nullptr, *drhs = nullptr;
+    CK(cudaMalloc(&dp, sizeof(double) * UCLGPU_NPARAM * ncell));
+    CK(cudaMalloc(&dy, sizeof(double) * NEQ * ncell));
+    CK(cudaMalloc(&dout, sizeof(double) * out_per_cell * ncell));
+    CK(cudaMemcpyAsync(dp, params, sizeof(double) * UCLGPU_NPARAM * ncell, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemcpyAsync(dy, y, sizeof(double) * NEQ * ncell, cudaMemcpyHostToDevice, d.stream));
+    if (rhs) {
+        CK(cudaMalloc(&drhs, sizeof(double) * NEQ * ncell));
+        CK(cudaMemcpyAsync(drhs, rhs, sizeof(double) * NEQ * ncell, cudaMemcpyHostToDevice, d.stream));
+    }
+    ProbeArgs a;
+    a.mode = mode; a.ncell = ncell; a.params = dp; a.y = dy; a.out = dout; a.gamma = gamma; a.rhs = drhs;
+    a.jsave = d.jsave;
+    k_probe<<<grid_blocks(d, ncell), NT, sizeof(Smem), d.stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, sizeof(double) * out_per_cell * ncell, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaFree(dp); cudaFree(dy); cudaFree(dout); cudaFree(drhs);
+    return 0;
+}
+
+extern "C" int uclgpu_get_rates(int64_t ncell, const double *params, const double *y, double *rates_out)
+{
+    return run_probe(0, ncell, params, y, rates_out, NREAC, 0.0, nullptr);
+}
+extern "C" int uclgpu_get_odes(int64_t ncell, const double *params, const double *y, double *ydot_out)
+{
+    return run_probe(2, ncell, params, y, ydot_out, NEQ, 0.0, nullptr);
+}
+// F(y) at the given state without the 1e-7 s pre-integration of get_odes (kernel-level parity tests)
+extern "C" int uclgpu_probe_rhs(int64_t ncell, const double *params, const double *y, double *ydot_out)
+{
+    return run_probe(1, ncell, params, y, ydot_out, NEQ, 0.0, nullptr);
+}
+// x = (I - gamma*J(y))^-1 b through the generated sparse LU; x_out is [ncell][naug] (old ordering)
+extern "C" int uclgpu_probe_newton(int64_t ncell, const double *params, const double *y, double gamma,
+                                   const double *b, double *x_out)
+{
+    if (!b) return UCLGPU_ERR_BAD_ARGUMENT;
+    return run_probe(3, ncell, params, y, x_out, NAUG, gamma, b);
+}
