@@ -1,0 +1,48 @@
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def net():
+    from uclchem_b200.network import load_default
+    return load_default()
+
+
+@pytest.fixture(scope="session")
+def oracle(net):
+    """The CPU restatement of the reference algorithm (test infrastructure)."""
+    from oracle.oracle import Oracle
+    return Oracle(net)
+
+
+@pytest.fixture(scope="session")
+def lib():
+    """The product: CUDA library behind the C ABI.  Fails loudly if it was not built."""
+    from uclchem_b200._capi import get_library
+    L = get_library("default")
+    L.init()
+    return L
+
+
+def max_dex(a, b, floor=1e-15):
+    """max |log10(a/b)| over entries of b above `floor` (the north-star parity metric)."""
+    a, b = np.asarray(a), np.asarray(b)
+    m = b > floor
+    return float(np.abs(np.log10(a[m] / b[m])).max())
+
+
+STATIC = {"endAtFinalDensity": False, "freefall": False, "initialDens": 1e4, "initialTemp": 10.0,
+          "finalDens": 1e5, "finalTime": 1.0e6}

@@ -28,7 +28,7 @@ EXPORTED = [
     "uclgpu_init", "uclgpu_shutdown", "uclgpu_strerror", "uclgpu_nspec", "uclgpu_nreac",
     "uclgpu_species_name", "uclgpu_network_tag", "uclgpu_default_params", "uclgpu_run_grid",
     "uclgpu_get_rates", "uclgpu_get_odes", "uclgpu_run_grid_device", "uclgpu_last_kernel_ms",
-    "uclgpu_naug", "uclgpu_probe_rhs", "uclgpu_probe_newton",
+    "uclgpu_naug", "uclgpu_probe_rhs", "uclgpu_probe_newton", "uclgpu_work_model", "uclgpu_fp64_peak",
 ]
 
 
@@ -78,6 +78,10 @@ class Library:
                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.uclgpu_last_kernel_ms.argtypes = [C.c_int, _pd, C.POINTER(C.c_int64)]
         L.uclgpu_init.argtypes = [C.c_int, _pi]
+        L.uclgpu_work_model.restype = C.c_int
+        L.uclgpu_work_model.argtypes = [_pd]
+        L.uclgpu_fp64_peak.restype = C.c_int
+        L.uclgpu_fp64_peak.argtypes = [C.c_int, _pd]
         self.nspec = L.uclgpu_nspec()
         self.nreac = L.uclgpu_nreac()
         self.neq = self.nspec + 1

@@ -1,0 +1,56 @@
+"""Build the CUDA library for one MakeRates network (in-tree, sm_100a only).
+
+``generate(tag)`` runs the MakeRates CUDA back-end on the network (from the
+reference's ``network.f90`` when a path is given, else from the committed
+``networks/<tag>.json``); ``compile(tag)`` runs nvcc.  The result is
+``uclchem_b200/lib/libuclgpu_<tag>.so`` -- one shared library per network, the way
+the reference compiles one ``uclchemwrap`` per network.
+"""
+from __future__ import annotations
+
+import shutil
+import subprocess
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+CSRC = _PKG / "csrc"
+LIBDIR = _PKG / "lib"
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def generate(tag: str = "default", network_f90: str | None = None) -> Path:
+    from .makerates_cuda import Generated, emit
+    from .network import Network
+
+    js = _PKG / "networks" / f"{tag}.json"
+    if network_f90 is not None:
+        net = Network.from_network_f90(network_f90)
+        js.parent.mkdir(parents=True, exist_ok=True)
+        net.to_json(js)
+    else:
+        net = Network.from_json(js)
+    return emit(Generated(net), CSRC / "generated" / tag, tag)
+
+
+def compile(tag: str = "default", force: bool = False, verbose: bool = False) -> Path:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    gen = CSRC / "generated" / tag / "net_tables.cuh"
+    if not gen.exists():
+        generate(tag)
+    LIBDIR.mkdir(exist_ok=True)
+    out = LIBDIR / f"libuclgpu_{tag}.so"
+    srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_bdf.cuh",
+            CSRC / "engine_model.cuh", gen, _PKG.parent / "include" / "uclgpu.h"]
+    if not force and out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
+        return out
+    cmd = [nvcc, *NVCC_FLAGS, f"-I{gen.parent}", "-o", str(out), str(CSRC / "uclgpu.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return out

@@ -120,6 +120,20 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
     }
 }
 
+// fp64 FMA peak micro-benchmark (roofline denominator for the fp64 pipe; MEASURED_PEAKS.json
+// only carries HBM and bf16 numbers)
+__global__ void k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
 // -------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------
@@ -213,6 +227,40 @@ extern "C" const char *uclgpu_strerror(int code)
     case UCLGPU_ERR_NOT_INITIALISED: return "uclgpu_init has not been called";
     }
     return "unknown error code";
+}
+
+extern "C" int uclgpu_work_model(double *out)
+{
+    // {F_rhs, F_jac, F_lu, F_solve, F_rates (flop per call), bytes per interval, 0, 0}
+    if (!out) return UCLGPU_ERR_BAD_ARGUMENT;
+    out[0] = NET_FLOP_RHS; out[1] = NET_FLOP_JAC; out[2] = NET_FLOP_LU; out[3] = NET_FLOP_SOLVE;
+    out[4] = NET_FLOP_RATES; out[5] = NET_BYTES_INTERVAL; out[6] = out[7] = 0.0;
+    return 0;
+}
+
+extern "C" int uclgpu_fp64_peak(int dev, double *tflops)
+{
+    if (!g_init) return UCLGPU_ERR_NOT_INITIALISED;
+    Device *d = nullptr;
+    for (auto &x : g_dev) if (x.id == dev) d = &x;
+    if (!d || !tflops) return UCLGPU_ERR_BAD_ARGUMENT;
+    CK(cudaSetDevice(d->id));
+    const int blocks = d->sms * 8, threads = 256, iters = 1 << 16;
+    double *buf = nullptr;
+    CK(cudaMalloc(&buf, sizeof(double) * blocks * threads));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(d->ev0, d->stream));
+        k_fp64_peak<<<blocks, threads, 0, d->stream>>>(buf, iters);
+        CK(cudaEventRecord(d->ev1, d->stream));
+        CK(cudaStreamSynchronize(d->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(buf);
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return 0;
 }
 
 extern "C" int uclgpu_nspec(void) { return NSPEC; }

@@ -395,6 +395,16 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     for k, v in d.items():
         w(f"#define {k} {v}\n")
     w(f'#define NET_TAG "{tag}"\n')
+    # algorithmic work per operation, counted from the generated tables
+    st_ = sym.stats
+    n_gather = int(len(sym.g_reac))
+    f_rhs = net.nreac * sym.fwidth + n_gather + 6 * len(net.surface_list)
+    f_jac = 4 * st_["j_terms"]
+    f_lu = 2 * st_["factor_terms"] + 2 * sym.m ** 3
+    f_solve = 2 * (st_["fwd_terms"] + st_["bwd_terms"] + st_["tail_terms"]) + 2 * sym.m ** 2
+    w(f"#define NET_FLOP_RHS {float(f_rhs)}\n#define NET_FLOP_JAC {float(f_jac)}\n#define NET_FLOP_LU {float(f_lu)}\n")
+    w(f"#define NET_FLOP_SOLVE {float(f_solve)}\n#define NET_FLOP_RATES {float(40 * net.nreac)}\n")
+    w(f"#define NET_BYTES_INTERVAL {float(2 * sym.neq * 8 + 64)}\n")
     for t in TYPE_NAMES:
         r = net.type_ranges[t]
         w(f"#define NET_{t}_LO {r[0] if r else -1}\n#define NET_{t}_HI {r[1] if r else -2}\n")

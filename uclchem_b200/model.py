@@ -1,0 +1,168 @@
+"""Host-side mirror of ``uclchem.model`` for the GPU path.
+
+Same names, argument meaning and return conventions as the reference
+(``src/uclchem/model.py``: ``cloud`` :227-316, ``hot_core`` :429-524, ``cshock``
+:527-644), but the work goes through the C ABI of ``include/uclgpu.h`` instead of
+``uclchemwrap``.  On top of the per-model functions the module adds what the
+reference leaves to user scripts (``scripts/grid.py:41-59``): ``cloud_grid``,
+``hot_core_grid`` and ``cshock_grid`` integrate a whole table of models in one call.
+
+Differences from the reference, all deliberate:
+
+* file based I/O (``outputFile``, ``abundSaveFile`` ...) is not part of the hot path
+  and is refused with the reference's own error; use the in-memory modes;
+* parameters start from ``defaultparameters.f90`` on every call (the reference leaks
+  parameters between calls);
+* a model failure is reported through the success flag, never raised
+  (``utils.check_error`` semantics, ``utils.py:30-51``).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from ._capi import N_PHYS, get_library
+from .params import MODEL_KINDS, params_from_dict
+
+TIMEPOINTS = 500  # src/uclchem/constants.py
+PHYSICAL_PARAMETERS = ["Time", "Density", "gasTemp", "dustTemp", "Av", "radfield", "zeta", "point"]
+
+
+def _lower(param_dict):
+    out = {}
+    for k, v in (param_dict or {}).items():
+        assert k.lower() not in out, f"Lower case key {k} is already in the dict, stopping"
+        out[k.lower()] = v
+    return out
+
+
+def pre_flight_checklist(return_array, return_dataframe, return_rates, starting_chemistry=None, user_params=None):
+    """model.py:103-155, minus the disk mode (which this path does not offer)."""
+    user_params = user_params or {}
+    if starting_chemistry is not None:
+        assert return_array or return_dataframe, (
+            "starting_chemistry can only be used with return_array or return_dataframe set to True;\n"
+            "Instead specify 'abundLoadFile' in the param_dict to load starting abundances from a file.")
+    file_keys = [k for k in user_params if k.lower().endswith("file")]
+    if file_keys:
+        raise RuntimeError("return_array or return_dataframe cannot be used if any output of input file is "
+                           "specified.\n" + f"Offending keys: {', '.join(file_keys)}")
+    if return_rates:
+        assert return_array or return_dataframe, (
+            "return_rates and return_heating can only be used with return_array or return_dataframe set to True; ")
+
+
+def _format_output(n_out, abunds, success_flag):
+    """model.py:76-81"""
+    abunds = [] if (success_flag < 0 or n_out == 0) else list(abunds[:n_out])
+    return [int(success_flag)] + abunds
+
+
+def _run_single(kind, param_dict, out_species, return_array, return_dataframe, return_rates, starting_chemistry,
+                timepoints, extra):
+    lib = get_library()
+    pd_ = _lower(param_dict)
+    pre_flight_checklist(return_array, return_dataframe, return_rates, starting_chemistry, pd_)
+    pd_.update(extra)
+    params = params_from_dict(pd_, ncell=1)
+    y0 = None
+    if starting_chemistry is not None:
+        sc = np.asarray(starting_chemistry, dtype=np.float64).ravel()
+        y0 = np.zeros((1, lib.neq))
+        y0[0, : lib.nspec] = sc[: lib.nspec]
+    traj = return_array or return_dataframe
+    out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if traj else 0,
+                       want_physics=traj, want_chem=traj, want_rates=traj and return_rates)
+    flag = int(out["flag"][0])
+    if not traj:
+        n_out = len(out_species) if out_species else 0
+        idx = [lib.species.index(s) for s in (out_species or [])]
+        res = _format_output(n_out, out["y_final"][0, idx], flag)
+        if kind == "cshock":
+            res = [res[0], float(out["dissipation_time"][0])] + res[1:]
+        return res
+    nrows = int(out["stats"][0][7]) + 1  # row 0 + one row per interval (model.py:158-187 trims by Time != 0)
+    nrows = min(nrows, timepoints + 1)
+    physics = out["physics"][0, :nrows][:, None, :]
+    chem = out["abund"][0, :nrows][:, None, :]
+    rates = out["rates"][0, :nrows][:, None, :] if return_rates else None
+    abundance_start = chem[nrows - 1, 0, :].copy()
+    if return_dataframe:
+        import pandas as pd
+
+        physics = pd.DataFrame(physics[:, 0, :N_PHYS], columns=PHYSICAL_PARAMETERS)
+        chem = pd.DataFrame(chem[:, 0, :], columns=lib.species)
+        if rates is not None:
+            rates = pd.DataFrame(rates[:, 0, :])
+    res = (physics, chem, rates, abundance_start)
+    if kind == "cshock":
+        res = res + (float(out["dissipation_time"][0]),)
+    return res + (flag,)
+
+
+def cloud(param_dict=None, out_species=None, return_array=False, return_dataframe=False, return_rates=False,
+          starting_chemistry=None, timepoints=TIMEPOINTS):
+    """Static or free-fall cloud (model.py:227-316)."""
+    return _run_single("cloud", param_dict, out_species, return_array, return_dataframe, return_rates,
+                       starting_chemistry, timepoints, {})
+
+
+def hot_core(temp_indx, max_temperature, param_dict=None, out_species=None, return_array=False,
+             return_dataframe=False, return_rates=False, starting_chemistry=None, timepoints=TIMEPOINTS):
+    """Hot core / hot corino warm-up (model.py:429-524)."""
+    return _run_single("hot_core", param_dict, out_species, return_array, return_dataframe, return_rates,
+                       starting_chemistry, timepoints, {"temp_indx": temp_indx, "max_temperature": max_temperature})
+
+
+def cshock(shock_vel, timestep_factor=0.01, minimum_temperature=0.0, param_dict=None, out_species=None,
+           return_array=False, return_dataframe=False, return_rates=False, starting_chemistry=None,
+           timepoints=TIMEPOINTS):
+    """C-type shock (model.py:527-644); returns the dissipation time like the reference."""
+    return _run_single("cshock", param_dict, out_species, return_array, return_dataframe, return_rates,
+                       starting_chemistry, timepoints,
+                       {"shock_vel": shock_vel, "timestep_factor": timestep_factor,
+                        "minimum_temperature": minimum_temperature})
+
+
+# ---------------------------------------------------------------------------------------
+# grids: what scripts/grid.py does with a process pool, in one call
+# ---------------------------------------------------------------------------------------
+def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None):
+    lib = get_library()
+    pd_ = _lower(param_dict)
+    pd_.update(extra)
+    params = params_from_dict(pd_)
+    ncell = params.shape[1]
+    y0 = None
+    if starting_chemistry is not None:
+        sc = np.asarray(starting_chemistry, dtype=np.float64)
+        if sc.ndim == 1:
+            sc = np.broadcast_to(sc, (ncell, sc.shape[0]))
+        y0 = np.zeros((ncell, lib.neq))
+        y0[:, : lib.nspec] = sc[:, : lib.nspec]
+    out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0)
+    res = {"flag": out["flag"], "abundances": out["y_final"][:, : lib.nspec], "physics": out["phys_final"],
+           "stats": out["stats"], "species": lib.species}
+    if out_species:
+        res["out_species"] = out["y_final"][:, [lib.species.index(s) for s in out_species]]
+    if kind == "cshock":
+        res["dissipation_time"] = out["dissipation_time"]
+    return res
+
+
+def cloud_grid(param_dict, starting_chemistry=None, out_species=None):
+    """Integrate a grid of cloud models.  Array-valued entries of ``param_dict`` are per-cell
+    columns, scalars broadcast.  Returns a dict with per-cell ``flag`` (constants.f90 codes),
+    final ``abundances`` [ncell, nspec], final ``physics`` [ncell, 8] and solver ``stats``."""
+    return _run_grid("cloud", param_dict, starting_chemistry, {}, out_species)
+
+
+def hot_core_grid(temp_indx, max_temperature, param_dict, starting_chemistry=None, out_species=None):
+    return _run_grid("hot_core", param_dict, starting_chemistry,
+                     {"temp_indx": temp_indx, "max_temperature": max_temperature}, out_species)
+
+
+def cshock_grid(shock_vel, param_dict, timestep_factor=0.01, minimum_temperature=0.0, starting_chemistry=None,
+                out_species=None):
+    return _run_grid("cshock", param_dict, starting_chemistry,
+                     {"shock_vel": shock_vel, "timestep_factor": timestep_factor,
+                      "minimum_temperature": minimum_temperature}, out_species)
