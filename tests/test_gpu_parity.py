@@ -99,15 +99,27 @@ def test_static_cloud_config1_against_golden(static_gpu):
 
 
 def test_element_and_charge_conservation(static_gpu, net, oracle):
+    """North-star: element (and charge) conservation to 1e-10 relative over the whole 1 Myr run.
+    Elements that every reaction conserves must be invariant outright.  H and charge are NOT
+    invariants of the reference RHS (protonated ions freeze out as their neutral, electrons
+    "freeze" at the H rate: SURVEY.md Q10); for those the drift must equal the oracle's drift."""
     out = static_gpu
     elements, counts, charge = net.element_matrix()
-    a0, a1 = out["abund"][0, 0], out["abund"][0, 46]
-    for e, row in zip(elements, counts):
-        assert abs(row @ a1 / (row @ a0) - 1) < CONS_TOL, e
-    # charge is NOT an invariant of the reference RHS: compare its drift with the oracle's
+    ls, lr, gs, gr = net.stoichiometry()
     ref = oracle.run_model(0, params_from_dict(STATIC)[:, 0])
-    q_gpu, q_ref = charge @ a1, charge @ ref["y_final"][:335]
-    assert abs(q_gpu - q_ref) <= 1e-6 * np.abs(charge * a1).sum()
+    a0, a1, r1 = out["abund"][0, 0], out["abund"][0, 46], ref["y_final"][:335]
+    exact = []
+    for e, row in list(zip(elements, counts)) + [("charge", charge)]:
+        imbalance = np.zeros(net.nreac)
+        np.add.at(imbalance, gr, row[gs])
+        np.add.at(imbalance, lr, -row[ls])
+        scale = np.abs(row * a0).sum()
+        if not imbalance.any():
+            exact.append(e)
+            assert abs(row @ a1 - row @ a0) < CONS_TOL * scale, e
+        else:
+            assert abs(row @ a1 - row @ r1) < CONS_TOL * scale, e
+    assert {"HE", "C", "N", "O", "S", "SI", "MG", "CL"} <= set(exact) and "H" not in exact
 
 
 def test_small_grid_against_oracle(lib, oracle, net):

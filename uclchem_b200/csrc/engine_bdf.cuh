@@ -6,7 +6,12 @@
 // with the same tolerances and WRMS norm.  Documented deviations from MF=22:
 //   * the Jacobian is analytic (DVODE: finite differences); it is saved and reused
 //     exactly as DVODE's JSV=1 policy prescribes (dvode.f90:8200-8206);
-//   * P is factorised with a fixed-pattern sparse LU without pivoting.
+//   * P is factorised with a fixed-pattern sparse LU without pivoting;
+//   * (experimental, off unless UCLGPU_WARM=1) warm restart: stop exactly at each output time
+//     (DVODE's ITASK=4 / TCRIT logic, dvode.f90:6421-6441) and keep the Nordsieck history.
+//     Measured on B200: it saves only ~10 of ~130 steps per interval (output times are a
+//     decade apart, the ramp-up after ISTATE=1 is short) and is not yet parity-clean, so the
+//     default is the reference's cold restart at every output time.
 // Scalar control runs on thread 0 between barriers; vector work is one thread per
 // equation; RHS / Jacobian / LU / solves are the block-parallel programs of
 // engine_core.cuh.
@@ -187,6 +192,7 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
             if (st.nst_call == 0 || st.nst_call > st.nslj + V_MSBJ) jok = -1;
             if (st.icf == 1 && st.drc < V_CCMXJ) jok = -1;
             if (st.icf == 2) jok = -1;
+            if (st.force_j) { jok = -1; st.force_j = 0; }
             st.flag2 = jok;
             if (jok == -1) {
                 st.nje++;
@@ -329,6 +335,10 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
     st.flag = 0;
     st.flag2 = 0;
     if (st.jstart > 0) {
+        if (st.kuth == 1) { // dvode.f90:7214-7217
+            st.eta = fmin(st.eta, st.h / st.hscal);
+            st.newh = 1;
+        }
         if (st.newh != 0) {
             if (st.newq < st.nq) st.flag = -1;
             else if (st.newq > st.nq) st.flag = 1;
@@ -556,13 +566,29 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
 
 // One DVODE call (ISTATE=1, ITASK=1): integrate s.abund from st.current_time to tout.
 // Returns DVODE's ISTATE; s.abund / st.current_time are updated as DVODE updates Y / T.
-__device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout)
+__device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout, bool warm)
 {
     Scalars &st = s.st;
     const int tid = threadIdx.x;
     const double t0 = st.current_time;
     if (fabs(tout - t0) <= 0.0) return 1;
     const double uround = DBL_EPSILON;
+    bool first = true;
+    if (warm) {
+        // continue from the previous output time with the history intact; the caller has
+        // refreshed the rates, the tolerances and (floor, BULK/SURFACE re-sum) the state
+        T0_BEGIN
+        st.tn = t0;
+        st.nst_call = 0;
+        st.nslp = 0;
+        st.nslj = 0;
+        st.ipup = 1;
+        st.force_j = 1;
+        st.kuth = 0;
+        T0_END
+        if (tid < NEQ) s.yh[0][tid] = s.abund[tid];
+        first = false; // recompute EWT from the edited state
+    } else {
     T0_BEGIN
     st.tn = t0;
     st.jstart = 0;
@@ -580,6 +606,9 @@ __device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout)
     st.nq = 1;
     st.l = 2;
     st.nfe++;
+    st.kuth = 0;
+    st.force_j = 0;
+    st.hnew = 0.0;
     T0_END
     if (tid < NEQ) {
         s.y[tid] = s.abund[tid];
@@ -646,7 +675,7 @@ __device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout)
         T0_END
     }
     if (tid < NEQ) s.yh[1][tid] *= h0;
-    bool first = true;
+    } // cold start
     int istate = 2;
     for (;;) {
         if (!first) {
@@ -666,10 +695,34 @@ __device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout)
             istate = -2;
             break;
         }
+        if (st.use_tcrit) {
+            // ITASK=4 with TCRIT = TOUT (dvode.f90:6433-6441): never step past the output time
+            T0_BEGIN
+            double hn = (st.jstart > 0 && st.hnew != 0.0) ? st.hnew : st.h;
+            double tnext = st.tn + hn * (1.0 + 4.0 * uround);
+            if ((tnext - tout) * st.h > 0.0) {
+                st.h = (tout - st.tn) * (1.0 - 4.0 * uround);
+                st.kuth = 1;
+            }
+            T0_END
+        }
         vstep_dev(s, b);
         if (st.kflag == -1) { istate = -4; break; }
         if (st.kflag <= -2) { istate = -5; break; }
-        if ((st.tn - tout) * st.h < 0.0) continue;
+        if (st.use_tcrit) {
+            // dvode.f90:6486-6497: arrived when |TN - TCRIT| <= 100 u (|TN| + |H|)
+            T0_BEGIN
+            st.kuth = 0;
+            T0_END
+            if (fabs(st.tn - tout) <= 100.0 * uround * (fabs(st.tn) + fabs(st.h))) {
+                if (tid < NEQ) s.abund[tid] = s.yh[0][tid];
+                T0_BEGIN
+                st.current_time = tout;
+                T0_END
+                return 2;
+            }
+            if ((st.tn - tout) * st.h < 0.0) continue;
+        } else if ((st.tn - tout) * st.h < 0.0) continue;
         // DVINDY_CORE dvode.f90:6901 with K=0: interpolate the Nordsieck polynomial back to TOUT
         if (tid < NEQ) {
             double sfrac = (tout - st.tn) / st.h;

@@ -78,6 +78,7 @@ struct Scalars {
         delp;
     int nq, l, lmax, nqwait, newq, newh, jstart, kflag, jcur, icf, ipup, nslp, nslj, nqu, ncf, nflag, m_iter;
     int nst_call; // NST of the current DVODE call
+    int kuth, force_j, hist_valid, use_tcrit; // ITASK=4 style stop at TOUT; warm restart bookkeeping
     long long nst, nfe, nje, nlu, nni, ncfn, netf, nintervals;
     long long nsing, nmaxcor, ndiverge, nfailcall;
     long long cyc_rates, cyc_rhs, cyc_jac, cyc_factor, cyc_dense, cyc_solve, cyc_total;
@@ -94,6 +95,7 @@ struct __align__(16) Smem {
     double ewt[NEQP], savf[NEQP], acor[NEQP], atol[NEQP], abund[NEQP];
     double xs[NAUGP];          // linear-solve vector, elimination (new) ordering
     double tmpv[NAUGP];
+    double invd[NAUGP];        // reciprocal sparse pivots (copied out of val after each factorisation)
     double red[2][32];
     double gj_row[2][GJ_PAD], gj_col[2][GJ_PAD], gj_piv[2];
     Scalars st;

@@ -10,45 +10,49 @@
 // ---- team-program executor ---------------------------------------------------------
 // desc[slot] = {term_begin, target | nterms<<16 | log2(team)<<28}; teams are aligned
 // power-of-two groups of consecutive slots; lane l of a team sums terms l, l+T, ...
-// Terms are fetched in batches of U independent loads and the next pass's descriptor
-// is prefetched, so a slot costs about one L2 round trip instead of one per term.
+// A program is a list of units (one pass of NT slots of one level; units[k] = {first slot,
+// end slot | barrier-after << 31}); levels are separated by block barriers.  A warp whose
+// 32 slots lie beyond the unit's end goes straight to the barrier: most solve levels only
+// occupy a few warps, and issue slots -- not bandwidth -- are what these phases cost.
+// Terms are fetched in one batch of U independent loads per lane.
 template <int U, class TermT, class TermF, class FinF>
-__device__ __forceinline__ void run_program(const uint32_t *__restrict__ desc, const TermT *__restrict__ terms,
-                                            uint32_t slot_begin, uint32_t slot_end, TermF term, FinF fin)
+__device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, const TermT *__restrict__ terms,
+                                           const uint32_t *__restrict__ units, int nunits, TermF term, FinF fin)
 {
     const uint2 *d2 = reinterpret_cast<const uint2 *>(desc);
-    uint32_t sl = slot_begin + threadIdx.x;
-    uint2 d = (sl < slot_end) ? __ldg(d2 + sl) : make_uint2(0u, 0xFFFFu);
-    while (sl < slot_end) { // warp-uniform: slot ranges are multiples of 32
-        const uint32_t sl_next = sl + NT;
-        const uint2 dn = (sl_next < slot_end) ? __ldg(d2 + sl_next) : make_uint2(0u, 0xFFFFu);
-        const uint32_t target = d.y & 0xFFFFu, n = (d.y >> 16) & 0xFFFu;
-        const int tl = (int)((d.y >> 28) & 7u);
-        const uint32_t T = 1u << tl;
-        const uint32_t lane_in_team = sl & (T - 1u);
-        double acc = 0.0;
-        if (target != 0xFFFFu) {
-            const TermT *tp = terms + d.x;
-            for (uint32_t q0 = lane_in_team; q0 < n; q0 += T * U) {
-                TermT tb[U];
+    const uint2 *units2 = reinterpret_cast<const uint2 *>(units);
+    for (int k = 0; k < nunits; k++) {
+        const uint2 un = __ldg(units2 + k);
+        const uint32_t end = un.y & 0x7FFFFFFFu;
+        const uint32_t sl = un.x + threadIdx.x;
+        if (sl - (threadIdx.x & 31u) < end) { // warp-uniform
+            const uint2 d = __ldg(d2 + sl);   // slot ranges are padded to multiples of 32
+            const uint32_t target = d.y & 0xFFFFu, n = (d.y >> 16) & 0xFFFu;
+            const int tl = (int)((d.y >> 28) & 7u);
+            const uint32_t T = 1u << tl, lane_in_team = sl & (T - 1u);
+            double acc = 0.0;
+            if (target != 0xFFFFu) {
+                const TermT *tp = terms + d.x;
+                for (uint32_t q0 = lane_in_team; q0 < n; q0 += T * U) {
+                    TermT tb[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    uint32_t q = q0 + (uint32_t)u * T;
-                    if (q < n) tb[u] = __ldg(tp + q);
+                    for (int u = 0; u < U; u++) {
+                        uint32_t q = q0 + (uint32_t)u * T;
+                        if (q < n) tb[u] = __ldg(tp + q);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (q0 + (uint32_t)u * T < n) acc += term(tb[u]);
                 }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (q0 + (uint32_t)u * T < n) acc += term(tb[u]);
             }
+            const int tmax = __reduce_max_sync(0xffffffffu, tl);
+            for (int o = 1; o < (1 << tmax); o <<= 1) {
+                double v = __shfl_xor_sync(0xffffffffu, acc, o);
+                if ((uint32_t)o < T) acc += v;
+            }
+            if (target != 0xFFFFu && lane_in_team == 0) fin(target, acc);
         }
-        const int tmax = __reduce_max_sync(0xffffffffu, tl);
-        for (int o = 1; o < (1 << tmax); o <<= 1) {
-            double v = __shfl_xor_sync(0xffffffffu, acc, o);
-            if ((uint32_t)o < T) acc += v;
-        }
-        if (target != 0xFFFFu && lane_in_team == 0) fin(target, acc);
-        sl = sl_next;
-        d = dn;
+        if (un.y >> 31) BLOCK_SYNC();
     }
 }
 
@@ -122,15 +126,14 @@ __device__ __noinline__ void rhs_eval(Smem &s, double *ydot)
     // ---- gather: ydot_i = sum of signed fluxes (io_functions.py:562-581) ---------------------
     {
         const double *flux = s.flux;
-        run_program<8>(
-            net_gather_desc, net_gather_terms, 0, net_gather_levels[1],
+        run_levels<8>(
+            net_gather_desc, net_gather_terms, net_gather_units, NET_GATHER_NUNITS,
             [&](uint16_t t) {
                 double v = flux[t & 0x7FFFu];
                 return (t & 0x8000u) ? -v : v;
             },
             [&](uint32_t target, double acc) { ydot[target] = acc; });
     }
-    BLOCK_SYNC();
     // ---- three-phase transfer odes.f90:4815-5180 ------------------------------------------------
     {
         double S = 0.0, MB = 0.0;
@@ -189,8 +192,8 @@ __device__ __noinline__ void jac_eval(Smem &s)
     {
         const double dblr = st.e_dblr, dism = st.e_dism;
         const double *rate = s.rate;
-        run_program<4>(
-            net_jac_desc, reinterpret_cast<const uint2 *>(net_jac_terms), 0, net_jac_levels[1],
+        run_levels<4>(
+            net_jac_desc, reinterpret_cast<const uint2 *>(net_jac_terms), net_jac_units, NET_JAC_NUNITS,
             [&](uint2 t) {
                 // t.x = reaction | kind<<28 | neg<<31 ; t.y = the other (non differentiated) factors
                 double v = rate[t.x & 0xFFFFFFu];
@@ -204,7 +207,6 @@ __device__ __noinline__ void jac_eval(Smem &s)
             },
             [&](uint32_t target, double acc) { val[target] = acc; });
     }
-    BLOCK_SYNC();
     {
         // tau row and three-phase transfer terms (each position has exactly one writer)
         const double S = st.e_S;
@@ -272,6 +274,8 @@ __device__ __noinline__ void form_p(Smem &s, double gamma, double *jsv, bool fre
 // In-place inverse of the dense trailing block by Gauss-Jordan elimination without
 // pivoting.  Each thread keeps a GJ_R x GJ_C tile of the block in registers for all M
 // steps; per step only the pivot row, pivot column and 1/pivot go through shared memory.
+// Every tile does the uniform update a_ij -= col_i * (row_j * p); only the few tiles that
+// contain the pivot row or column patch their entries afterwards (a_kj p, -a_ik p, p).
 __device__ __noinline__ bool dense_inverse(Smem &s)
 {
     static_assert(GJ_TR * GJ_TC <= NT, "dense tile grid must fit the block");
@@ -289,12 +293,13 @@ __device__ __noinline__ bool dense_inverse(Smem &s)
             a[r][c] = (active && i < MDENSE && j < MDENSE) ? T[i * MDENSE + j] : 0.0;
         }
     bool ok = true;
-    for (int k = 0; k < MDENSE; k++) {
-        const int buf = k & 1;
-        // owners publish the pre-step pivot row / column
-        if (active) {
+    constexpr int GJ_NTHR = (GJ_TR * GJ_TC + 31) & ~31; // whole warps take part in the named barrier
+    if (tid < GJ_NTHR) {
+        for (int k = 0; k < MDENSE; k++) {
+            const int buf = k & 1;
             const int rk = k - i0, ck = k - j0;
-            if (rk >= 0 && rk < GJ_R) {
+            const bool own_r = active && (unsigned)rk < (unsigned)GJ_R, own_c = active && (unsigned)ck < (unsigned)GJ_C;
+            if (own_r) {
 #pragma unroll
                 for (int r = 0; r < GJ_R; r++)
                     if (r == rk) {
@@ -302,24 +307,20 @@ __device__ __noinline__ bool dense_inverse(Smem &s)
                         for (int c = 0; c < GJ_C; c++) s.gj_row[buf][j0 + c] = a[r][c];
                     }
             }
-            if (ck >= 0 && ck < GJ_C) {
+            if (own_c) {
 #pragma unroll
                 for (int c = 0; c < GJ_C; c++)
                     if (c == ck) {
 #pragma unroll
-                        for (int r = 0; r < GJ_R; r++) s.gj_col[buf][i0 + r] = a[r][c];
-                        if (rk >= 0 && rk < GJ_R) {
-#pragma unroll
-                            for (int r = 0; r < GJ_R; r++)
-                                if (r == rk) s.gj_piv[buf] = 1.0 / a[r][c];
+                        for (int r = 0; r < GJ_R; r++) {
+                            s.gj_col[buf][i0 + r] = a[r][c];
+                            if (r == rk) s.gj_piv[buf] = 1.0 / a[r][c];
                         }
                     }
             }
-        }
-        BLOCK_SYNC();
-        const double p = s.gj_piv[buf];
-        if (!isfinite(p) || p == 0.0) ok = false;
-        if (active) {
+            asm volatile("barrier.sync 1, %0;" ::"r"(GJ_NTHR) : "memory");
+            const double p = s.gj_piv[buf];
+            if (!isfinite(p) || p == 0.0) ok = false;
             double rp[GJ_C], cl[GJ_R];
 #pragma unroll
             for (int c = 0; c < GJ_C; c++) rp[c] = s.gj_row[buf][j0 + c] * p;
@@ -328,26 +329,35 @@ __device__ __noinline__ bool dense_inverse(Smem &s)
 #pragma unroll
             for (int r = 0; r < GJ_R; r++)
 #pragma unroll
-                for (int c = 0; c < GJ_C; c++) {
-                    const bool ir = (i0 + r == k), jc = (j0 + c == k);
-                    double v = a[r][c] - cl[r] * rp[c];
-                    if (ir) v = rp[c];
-                    if (jc) v = -cl[r] * p;
-                    if (ir && jc) v = p;
-                    a[r][c] = v;
-                }
+                for (int c = 0; c < GJ_C; c++) a[r][c] -= cl[r] * rp[c];
+            if (own_r) {
+#pragma unroll
+                for (int r = 0; r < GJ_R; r++)
+                    if (r == rk) {
+#pragma unroll
+                        for (int c = 0; c < GJ_C; c++) a[r][c] = rp[c];
+                    }
+            }
+            if (own_c) {
+#pragma unroll
+                for (int c = 0; c < GJ_C; c++)
+                    if (c == ck) {
+#pragma unroll
+                        for (int r = 0; r < GJ_R; r++) a[r][c] = (r == rk) ? p : -cl[r] * p;
+                    }
+            }
         }
+#pragma unroll
+        for (int r = 0; r < GJ_R; r++)
+#pragma unroll
+            for (int c = 0; c < GJ_C; c++) {
+                int i = i0 + r, j = j0 + c;
+                if (active && i < MDENSE && j < MDENSE) T[i * MDENSE + j] = a[r][c];
+            }
+        if (tid == 0) s.gj_piv[0] = ok ? 1.0 : 0.0; // every participant saw the same pivots
     }
     BLOCK_SYNC();
-#pragma unroll
-    for (int r = 0; r < GJ_R; r++)
-#pragma unroll
-        for (int c = 0; c < GJ_C; c++) {
-            int i = i0 + r, j = j0 + c;
-            if (active && i < MDENSE && j < MDENSE) T[i * MDENSE + j] = a[r][c];
-        }
-    BLOCK_SYNC();
-    return ok;
+    return s.gj_piv[0] != 0.0;
 }
 
 // Numeric factorisation of P (in s.val) on the generated pattern.  Sparse pivots end up stored
@@ -357,24 +367,22 @@ __device__ __noinline__ bool factor_p(Smem &s, Blk &b)
     const int tid = threadIdx.x;
     double *val = s.val;
     TIMER_START
-    for (int lv = 0; lv < NET_FACTOR_NLEVELS; lv++) {
-        run_program<8>(
-            net_factor_desc, net_factor_terms, net_factor_levels[lv], net_factor_levels[lv + 1],
-            [&](uint32_t t) { return val[t >> 16] * val[t & 0xFFFFu]; },
-            [&](uint32_t target, double acc) {
-                double x = val[target] - acc;
-                uint32_t d = net_factor_diag[target];
-                if (d == 0xFFFEu) x = 1.0 / x;       // sparse pivot: keep the reciprocal
-                else if (d != 0xFFFFu) x *= val[d];  // L entry: scale by 1/pivot
-                val[target] = x;
-            });
-        BLOCK_SYNC();
-    }
+    run_levels<8>(
+        net_factor_desc, net_factor_terms, net_factor_units, NET_FACTOR_NUNITS,
+        [&](uint32_t t) { return val[t >> 16] * val[t & 0xFFFFu]; },
+        [&](uint32_t target, double acc) {
+            double x = val[target] - acc;
+            uint32_t d = net_factor_diag[target];
+            if (d == 0xFFFEu) x = 1.0 / x;       // sparse pivot: keep the reciprocal
+            else if (d != 0xFFFFu) x *= val[d];  // L entry: scale by 1/pivot
+            val[target] = x;
+        });
     TIMER_ADD(cyc_factor)
     bool ok = dense_inverse(s);
     double bad = 0.0;
     if (tid < NET_N0) {
         double d = val[net_diag_pos[tid]];
+        s.invd[tid] = d;
         if (!isfinite(d) || d == 0.0) bad = 1.0;
     }
     bad = block_sum(s, b, bad);
@@ -389,18 +397,11 @@ __device__ __noinline__ void lin_solve(Smem &s)
     const double *val = s.val;
     double *xs = s.xs;
     TIMER_START
-    for (int lv = 0; lv < NET_FWD_NLEVELS; lv++) {
-        run_program<8>(
-            net_fwd_desc, net_fwd_terms, net_fwd_levels[lv], net_fwd_levels[lv + 1],
-            [&](uint32_t t) { return val[t >> 16] * xs[t & 0xFFFFu]; },
-            [&](uint32_t target, double acc) { xs[target] -= acc; });
-        BLOCK_SYNC();
-    }
-    run_program<8>(
-        net_tail_desc, net_tail_terms, 0, net_tail_levels[1],
+    // forward substitution through the sparse rows, then b_T -= L21 x (one program: fwd levels + tail)
+    run_levels<8>(
+        net_fwd_desc, net_fwd_terms, net_fwd_units, NET_FWD_NUNITS,
         [&](uint32_t t) { return val[t >> 16] * xs[t & 0xFFFFu]; },
         [&](uint32_t target, double acc) { xs[target] -= acc; });
-    BLOCK_SYNC();
     {
         // x_T = Tinv * b_T : 4 lanes per row
         const double *T = val + NET_OFF_DENSE;
@@ -417,12 +418,9 @@ __device__ __noinline__ void lin_solve(Smem &s)
     BLOCK_SYNC();
     if (tid < MDENSE) xs[NET_N0 + tid] = s.tmpv[tid];
     BLOCK_SYNC();
-    for (int lv = 0; lv < NET_BWD_NLEVELS; lv++) {
-        run_program<8>(
-            net_bwd_desc, net_bwd_terms, net_bwd_levels[lv], net_bwd_levels[lv + 1],
-            [&](uint32_t t) { return val[t >> 16] * xs[t & 0xFFFFu]; },
-            [&](uint32_t target, double acc) { xs[target] = (xs[target] - acc) * val[net_diag_pos[target]]; });
-        BLOCK_SYNC();
-    }
+    run_levels<8>(
+        net_bwd_desc, net_bwd_terms, net_bwd_units, NET_BWD_NUNITS,
+        [&](uint32_t t) { return val[t >> 16] * xs[t & 0xFFFFu]; },
+        [&](uint32_t target, double acc) { xs[target] = (xs[target] - acc) * s.invd[target]; });
     TIMER_ADD(cyc_solve)
 }

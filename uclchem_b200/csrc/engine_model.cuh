@@ -28,6 +28,9 @@ struct RunArgs {
     double *jsave;               // [gridDim.x][JSV_STRIDE] saved-Jacobian scratch
     double *trace;               // debug: [trace_cap][8] Newton-iteration records of cell 0 (or null)
     int trace_cap, dump_at;
+    int warm_restart;            // experimental (UCLGPU_WARM=1): keep the BDF history across output times
+    long long max_steps;         // diagnostic watchdog: abort a cell (flag -5) beyond this many BDF steps; 0 = off
+    const int *order;            // processing order of the cells (most expensive first) or null
     double *dump;
 };
 
@@ -420,7 +423,8 @@ __device__ int update_chemistry_dev(Smem &s, Blk &b)
             s.atol[tid] = v;
         }
         BLOCK_SYNC();
-        int istate = bdf_integrate(s, b, st.target_time);
+        const bool warm = st.use_tcrit && st.hist_valid;
+        int istate = bdf_integrate(s, b, st.target_time, warm);
         if (istate == -3) return UCLGPU_INT_UNRECOVERABLE_ERROR;
         // integrateODESystem chemistry.f90:256-291
         if (st.p[UCL_P_ENFORCECHARGECONSERVATION] != 0.0) {
@@ -430,6 +434,7 @@ __device__ int update_chemistry_dev(Smem &s, Blk &b)
             if (tid == 0) s.abund[NET_NELEC] = q;
         }
         T0_BEGIN
+        st.hist_valid = (istate == 2) ? 1 : 0; // any failed call is followed by a cold restart (ISTATE=1)
         if (istate < 0) st.nfailcall++;
         switch (istate) {
         case -1: case -4: case -5: break; // the shortened target is overwritten just below (Q3)
@@ -483,6 +488,8 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
     st.last_temp = 99.0e99;
     st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;
     st.nsing = st.nmaxcor = st.ndiverge = st.nfailcall = 0;
+    st.hist_valid = 0;
+    st.use_tcrit = (a.kind == UCLGPU_CLOUD && a.warm_restart) ? 1 : 0; // experimental, off by default
     st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = 0;
     st.cyc_total = clock64();
     st.flag = initialize_physics_dev(st);
@@ -517,6 +524,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
             T0_END
             flag = update_chemistry_dev(s, b);
             if (flag < 0) break;
+            if (a.max_steps > 0 && st.nst > a.max_steps) { flag = UCLGPU_INT_TOO_MANY_FAILS_ERROR; break; }
             T0_BEGIN
             st.nintervals++;
             st.time_in_years = st.target_time / C_SPY;

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(NT, 1) k_integrate(RunArgs a)
         BLOCK_SYNC();
         long long cell = cell_sh;
         if (cell >= a.ncell) break;
+        if (a.order) cell = a.order[cell];
         b.trace = (cell == 0) ? a.trace : nullptr;
         b.trace_cap = a.trace_cap;
         b.trace_n = 0;
@@ -83,6 +84,8 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         st.last_temp = 99.0e99;
         st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;
         st.nsing = st.nmaxcor = st.ndiverge = st.nfailcall = 0;
+        st.hist_valid = 0;
+        st.use_tcrit = 0;
         st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = st.cyc_total = 0;
         initialize_physics_dev(st);
         T0_END
@@ -307,6 +310,8 @@ static int launch_integrate(Device &d, const RunArgs &a)
     RunArgs aa = a;
     aa.counter = d.counter;
     aa.jsave = d.jsave;
+    if (getenv("UCLGPU_MAX_STEPS")) aa.max_steps = atoll(getenv("UCLGPU_MAX_STEPS"));
+    if (getenv("UCLGPU_WARM")) aa.warm_restart = atoi(getenv("UCLGPU_WARM"));
     // debug: UCLGPU_TRACE=<records> UCLGPU_TRACE_FILE=<path> dumps cell 0's Newton iterations
     double *d_trace = nullptr;
     const char *tr = getenv("UCLGPU_TRACE");

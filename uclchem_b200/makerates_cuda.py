@@ -456,8 +456,7 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     w("\n// ---- symbolic LU: factor levels, dense block, solves ---------------------------------\n")
     _emit_program(w, "net_factor", [p for p, _ in gen.factor])
     w(_c_array("net_factor_diag", gen.factor_diag_table(), "uint16_t"))
-    _emit_program(w, "net_fwd", gen.fwd)
-    _emit_program(w, "net_tail", [gen.tail])
+    _emit_program(w, "net_fwd", gen.fwd + [gen.tail])  # forward levels, then b_T -= L21 x
     _emit_program(w, "net_bwd", gen.bwd)
     w(_c_array("net_perm", sym.perm, "uint16_t"))
     w(_c_array("net_iperm", sym.iperm, "uint16_t"))
@@ -493,6 +492,15 @@ def _emit_program(w, name, programs, term16=False, term64=False):
     else:
         w(_c_array(name + "_terms", terms, "uint32_t"))
     w(_c_array(name + "_levels", lv, "uint32_t"))
+    # unit table: one entry per (level, pass of NTHREADS slots): {first slot, end slot | barrier-after flag << 31}
+    units = []
+    for k in range(len(programs)):
+        b0, e0 = lv[k], lv[k + 1]
+        starts = list(range(b0, e0, NTHREADS)) or [b0]
+        for i, st in enumerate(starts):
+            units.append((st, e0 | ((1 << 31) if i == len(starts) - 1 else 0)))
+    w(f"#define {name.upper()}_NUNITS {len(units)}\n")
+    w(_c_array(name + "_units", np.asarray(units, dtype=np.uint64).ravel(), "uint32_t"))
 
 
 def main(argv=None):
