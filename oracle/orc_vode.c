@@ -386,8 +386,8 @@ static int vnls(vode_t *s, int *nflag)
             if (m != 0) s->crate = fmax(CRDOWN * s->crate, del / delp);
             double dcon = del * fmin(1.0, s->crate) / s->tq[4];
             if (s->trace)
-                fprintf((FILE *)s->trace, "%.17g %.17g %d %d %.6e %.6e %.6e %ld.%d\n", s->tn, s->h, s->nq, m, del, dcon, s->rc,
-                        s->nst, s->jcur);
+                fprintf((FILE *)s->trace, "%.17g %.17g %d %d %.6e %.6e %.6e %ld.%d %.6e %.6e\n", s->tn, s->h, s->nq, m, del, dcon, s->rc,
+                        s->nst, s->jcur, y[n - 2], y[n - 3]);
             if (dcon <= 1.0) { /* label 80 */
                 *nflag = 0;
                 s->jcur = 0;

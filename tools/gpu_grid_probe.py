@@ -22,4 +22,5 @@ for k in order[:12]:
     print(f"cell {idx[k]} dens {p[PARAM_INDEX['initialdens'],k]:.2e} T {p[PARAM_INDEX['initialtemp'],k]:.0f} zeta {p[PARAM_INDEX['zeta'],k]:.1f} sec {cyc[k]:.2f} nst {S['nst'][k]} nlu {S['nlu'][k]} nje {S['nje'][k]} ncfn {S['ncfn'][k]} netf {S['netf'][k]} failcalls {S['nfailcall'][k]} nsing {S['nsing'][k]}")
 tot = {k: S[k].sum() for k in ('cyc_rates','cyc_rhs','cyc_jac','cyc_factor','cyc_dense','cyc_solve','cyc_total')}
 print({k: round(v/tot['cyc_total'],3) for k,v in tot.items()})
+np.savez('gpurun_out/grid_stats_%d.npz' % n, idx=idx, params=p, stats=st, flag=o['flag'], y_final=o['y_final'], kernel_ms=ms)
 print('mean nst', S['nst'].mean(), 'mean nlu', S['nlu'].mean(), 'mean nni', S['nni'].mean(), 'mean nfe', S['nfe'].mean())

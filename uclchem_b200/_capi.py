@@ -38,7 +38,7 @@ class UclgpuStats(C.Structure):
 
 class UclgpuOpts(C.Structure):
     _fields_ = [("timepoints", C.c_int32), ("physics_traj", _pd), ("chem_traj", _pd), ("rates_traj", _pd),
-                ("dissipation_time", _pd), ("keep_on_device", C.c_int32), ("reserved", C.c_int32)]
+                ("dissipation_time", _pd), ("keep_on_device", C.c_int32), ("step_budget", C.c_int32)]
 
 
 class UclgpuError(RuntimeError):
@@ -110,7 +110,7 @@ class Library:
         return out
 
     def run_grid(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 0, want_physics=False,
-                 want_chem=False, want_rates=False):
+                 want_chem=False, want_rates=False, step_budget: int = 0):
         params = np.ascontiguousarray(params, np.float64)
         assert params.ndim == 2 and params.shape[0] == NPARAM
         ncell = params.shape[1]
@@ -125,6 +125,7 @@ class Library:
             y0p = y0.ctypes.data_as(_pd)
         opts = UclgpuOpts()
         opts.timepoints = timepoints
+        opts.step_budget = step_budget
         out = {}
         tdiss = np.zeros(ncell)
         opts.dissipation_time = tdiss.ctypes.data_as(_pd)

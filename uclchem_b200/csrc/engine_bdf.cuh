@@ -225,11 +225,11 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
             if (tid < NAUG) {
                 int o = net_perm[tid];
                 double v = 0.0;
-                if (o < NEQ && o != NET_IB && o != NET_IS)
-                    v = (st.rl1 * st.h) * s.savf[o] - (st.rl1 * s.yh[1][o] + s.acor[o]);
+                if (o < NEQ) v = (st.rl1 * st.h) * s.savf[o] - (st.rl1 * s.yh[1][o] + s.acor[o]);
                 s.xs[tid] = v;
             }
             BLOCK_SYNC();
+            constraint_rhs(s);
             const bool dump = b.trace && b.dump && b.trace_n == b.dump_at;
             if (dump) {
                 double *D = b.dump;
@@ -270,7 +270,8 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
             if (st.m_iter != 0) st.crate = fmax(V_CRDOWN * st.crate, del / st.delp);
             double dcon = del * fmin(1.0, st.crate) / st.tq[4];
             if (b.trace && b.trace_n < b.trace_cap) {
-                double *r = b.trace + 8 * (size_t)b.trace_n;
+                double *r = b.trace + 12 * (size_t)b.trace_n;
+                r[8] = s.y[NET_IS]; r[9] = s.y[NET_IB]; r[10] = st.e_S; r[11] = s.yh[0][NET_IS];
                 r[0] = st.tn; r[1] = st.h; r[2] = st.nq; r[3] = st.m_iter; r[4] = del; r[5] = dcon; r[6] = st.rc;
                 r[7] = (double)st.nst_call + 1e-3 * st.jcur;
             }

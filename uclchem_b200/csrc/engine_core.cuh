@@ -65,6 +65,7 @@ struct Scalars {
     // per-interval rate prefactors
     double k_desoh2, k_descr, k_deuvcr, stick_h, stick_h2, h2form_dust, scat_h2_pre, thermal_vel;
     int lh_on, swap_off, mxstep, kind;
+    long long step_budget;
     // RHS ext quantities at the last evaluated state
     double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S;
     // hotcore / cshock

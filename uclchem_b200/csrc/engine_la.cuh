@@ -271,6 +271,27 @@ __device__ __noinline__ void form_p(Smem &s, double gamma, double *jsv, bool fre
     TIMER_ADD(cyc_jac)
 }
 
+// Right-hand side of the two constraint rows of the bordered Newton system.  The rows of BULK and
+// SURFACE in P = I - gamma*J are the sums of their members' rows (odes.f90:5155-5180 defines their
+// ydot as those sums), so the generated system stores them as  dBULK - sum_b d_b = r_BULK - sum_b r_b.
+// On entry s.xs holds the plain residual r of every equation (new ordering); this replaces the two
+// constraint entries by r - sum(members).  Dropping the right-hand side (i.e. d = sum of members)
+// would leave the Nordsieck history of BULK/SURFACE uncorrected: rounding-level content in its
+// higher columns is then amplified by every step-size increase (eta^j) and the variable drifts away
+// from the sum of its members.  Ends with a barrier.
+__device__ __forceinline__ void constraint_rhs(Smem &s)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < 2) {
+        const int16_t *list = warp == 0 ? net_surface_list : net_bulk_list;
+        double acc = 0.0;
+        for (int k = lane; k < NSURF; k += 32) acc += s.xs[net_iperm[list[k]]];
+        acc = warp_sum(acc);
+        if (lane == 0) s.xs[net_iperm[warp == 0 ? NET_IS : NET_IB]] -= acc;
+    }
+    BLOCK_SYNC();
+}
+
 // In-place inverse of the dense trailing block by Gauss-Jordan elimination without
 // pivoting.  Each thread keeps a GJ_R x GJ_C tile of the block in registers for all M
 // steps; per step only the pivot row, pivot column and 1/pivot go through shared memory.

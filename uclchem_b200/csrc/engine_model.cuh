@@ -29,7 +29,7 @@ struct RunArgs {
     double *trace;               // debug: [trace_cap][8] Newton-iteration records of cell 0 (or null)
     int trace_cap, dump_at;
     int warm_restart;            // experimental (UCLGPU_WARM=1): keep the BDF history across output times
-    long long max_steps;         // diagnostic watchdog: abort a cell (flag -5) beyond this many BDF steps; 0 = off
+    long long max_steps;         // uclgpu_opts.step_budget: abandon a cell (flag -5) beyond this many BDF steps; 0 = off
     const int *order;            // processing order of the cells (most expensive first) or null
     double *dump;
 };
@@ -426,6 +426,7 @@ __device__ int update_chemistry_dev(Smem &s, Blk &b)
         const bool warm = st.use_tcrit && st.hist_valid;
         int istate = bdf_integrate(s, b, st.target_time, warm);
         if (istate == -3) return UCLGPU_INT_UNRECOVERABLE_ERROR;
+        if (st.step_budget > 0 && st.nst > st.step_budget) return UCLGPU_INT_TOO_MANY_FAILS_ERROR;
         // integrateODESystem chemistry.f90:256-291
         if (st.p[UCL_P_ENFORCECHARGECONSERVATION] != 0.0) {
             double q = 0.0;
@@ -484,6 +485,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
     st.phi = st.p[UCL_P_PHI];
     st.abstol_factor = st.p[UCL_P_ABSTOL_FACTOR];
     st.mxstep = (int)st.p[UCL_P_MXSTEP];
+    st.step_budget = a.max_steps;
     st.rtol = st.p[UCL_P_RELTOL];
     st.last_temp = 99.0e99;
     st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;
@@ -524,7 +526,6 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
             T0_END
             flag = update_chemistry_dev(s, b);
             if (flag < 0) break;
-            if (a.max_steps > 0 && st.nst > a.max_steps) { flag = UCLGPU_INT_TOO_MANY_FAILS_ERROR; break; }
             T0_BEGIN
             st.nintervals++;
             st.time_in_years = st.target_time / C_SPY;

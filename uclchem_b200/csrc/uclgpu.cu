@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "engine_model.cuh"
@@ -115,9 +116,10 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         bool ok = factor_p(s, b);
         if (tid < NAUG) {
             int o = net_perm[tid];
-            s.xs[tid] = (o < NEQ && o != NET_IB && o != NET_IS) ? a.rhs[(size_t)cell * NEQ + o] : 0.0;
+            s.xs[tid] = (o < NEQ) ? a.rhs[(size_t)cell * NEQ + o] : 0.0;
         }
         BLOCK_SYNC();
+        constraint_rhs(s);
         lin_solve(s);
         for (int i = tid; i < NAUG; i += NT) a.out[(size_t)cell * NAUG + i] = ok ? s.xs[net_iperm[i]] : nan("");
     }
@@ -317,8 +319,8 @@ static int launch_integrate(Device &d, const RunArgs &a)
     const char *tr = getenv("UCLGPU_TRACE");
     int cap = tr ? atoi(tr) : 0;
     if (cap > 0) {
-        CK(cudaMalloc(&d_trace, sizeof(double) * 8 * (size_t)cap));
-        CK(cudaMemsetAsync(d_trace, 0, sizeof(double) * 8 * (size_t)cap, d.stream));
+        CK(cudaMalloc(&d_trace, sizeof(double) * 12 * (size_t)cap));
+        CK(cudaMemsetAsync(d_trace, 0, sizeof(double) * 12 * (size_t)cap, d.stream));
         aa.trace = d_trace;
         aa.trace_cap = cap;
     }
@@ -335,7 +337,7 @@ static int launch_integrate(Device &d, const RunArgs &a)
     CK(cudaEventRecord(d.ev1, d.stream));
     CK(cudaGetLastError());
     if (cap > 0) {
-        std::vector<double> h(8 * (size_t)cap);
+        std::vector<double> h(12 * (size_t)cap);
         CK(cudaMemcpyAsync(h.data(), d_trace, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, d.stream));
         CK(cudaStreamSynchronize(d.stream));
         const char *fn = getenv("UCLGPU_TRACE_FILE");
@@ -393,13 +395,36 @@ struct DevBuf {
     double *params = nullptr, *y0 = nullptr, *y_final = nullptr, *phys = nullptr, *ptraj = nullptr, *ctraj = nullptr,
            *rtraj = nullptr, *tdiss = nullptr;
     int32_t *flag = nullptr;
+    int *order = nullptr;
     uclgpu_stats *stats = nullptr;
     void release()
     {
-        cudaFree(params); cudaFree(y0); cudaFree(y_final); cudaFree(phys); cudaFree(ptraj); cudaFree(ctraj);
+        cudaFree(order); cudaFree(params); cudaFree(y0); cudaFree(y_final); cudaFree(phys); cudaFree(ptraj); cudaFree(ctraj);
         cudaFree(rtraj); cudaFree(tdiss); cudaFree(flag); cudaFree(stats);
     }
 };
+
+// Relative cost estimate of one cell from its parameters (measured on the config-2 grid: the step
+// count grows with density and cosmic-ray rate and falls with temperature; DESIGN.md "load balance").
+static std::vector<int> cost_order(const double *params, int64_t ncell, long long lo, long long n)
+{
+    std::vector<double> key(n);
+    for (long long c = 0; c < n; c++) {
+        const double dens = params[(size_t)UCL_P_INITIALDENS * ncell + lo + c];
+        const double fdens = params[(size_t)UCL_P_FINALDENS * ncell + lo + c];
+        const double ff = params[(size_t)UCL_P_FREEFALL * ncell + lo + c];
+        const double zeta = params[(size_t)UCL_P_ZETA * ncell + lo + c];
+        const double temp = params[(size_t)UCL_P_INITIALTEMP * ncell + lo + c];
+        const double tfin = params[(size_t)UCL_P_FINALTIME * ncell + lo + c];
+        const double nn = (ff != 0.0 && fdens > dens) ? fdens : dens;
+        key[c] = log10(nn > 1.0 ? nn : 1.0) + 0.5 * log10(zeta > 1e-3 ? zeta : 1e-3) - 0.01 * temp +
+                 0.2 * log10(tfin > 1.0 ? tfin : 1.0);
+    }
+    std::vector<int> ord(n);
+    for (long long c = 0; c < n; c++) ord[c] = (int)c;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return key[x] > key[y]; });
+    return ord;
+}
 
 extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const double *params, const double *y0,
                                double *y_final, double *phys_final, int32_t *flag, uclgpu_stats *stats,
@@ -441,7 +466,17 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
             memset(&a, 0, sizeof(a));
             a.kind = (int)kind; a.ncell = n; a.params = B.params; a.y0 = B.y0; a.y_final = B.y_final;
             a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
+            if (n > d.sms) {
+                // longest-expected-first processing order: the CTAs pull cells from one counter, so
+                // starting the expensive cells first keeps the tail of the launch short
+                std::vector<int> ord = cost_order(params, ncell, lo[i], n);
+                CK(cudaMalloc(&B.order, sizeof(int) * n));
+                CK(cudaMemcpyAsync(B.order, ord.data(), sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
+                CK(cudaStreamSynchronize(d.stream)); // ord goes out of scope
+                a.order = B.order;
+            }
             if (opts) {
+                a.max_steps = opts->step_budget;
                 a.timepoints = opts->timepoints;
                 if (opts->physics_traj) { CK(cudaMalloc(&B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n)); CK(cudaMemsetAsync(B.ptraj, 0, sizeof(double) * UCLGPU_NPHYS * T1 * n, d.stream)); a.phys_traj = B.ptraj; }
                 if (opts->chem_traj) { CK(cudaMalloc(&B.ctraj, sizeof(double) * NSPEC * T1 * n)); CK(cudaMemsetAsync(B.ctraj, 0, sizeof(double) * NSPEC * T1 * n, d.stream)); a.chem_traj = B.ctraj; }
