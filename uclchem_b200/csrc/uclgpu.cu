@@ -357,6 +357,31 @@ static int launch_integrate(Device &d, const RunArgs &a)
     return 0;
 }
 
+// Relative cost estimate of one cell from its parameters (measured on the config-2 grid: the step
+// count grows with density and cosmic-ray rate and falls with temperature; DESIGN.md "load balance").
+static std::vector<int> cost_order(const double *params, int64_t ncell, long long lo, long long n)
+{
+    std::vector<double> key(n);
+    for (long long c = 0; c < n; c++) {
+        const double dens = params[(size_t)UCL_P_INITIALDENS * ncell + lo + c];
+        const double fdens = params[(size_t)UCL_P_FINALDENS * ncell + lo + c];
+        const double ff = params[(size_t)UCL_P_FREEFALL * ncell + lo + c];
+        const double zeta = params[(size_t)UCL_P_ZETA * ncell + lo + c];
+        const double temp = params[(size_t)UCL_P_INITIALTEMP * ncell + lo + c];
+        const double tfin = params[(size_t)UCL_P_FINALTIME * ncell + lo + c];
+        const double nn = (ff != 0.0 && fdens > dens) ? fdens : dens;
+        key[c] = log10(nn > 1.0 ? nn : 1.0) + 0.2 * log10(tfin > 1.0 ? tfin : 1.0) + 0.01 * temp;
+        // the two regions of the config-2 grid where DVODE keeps hitting MXSTEP (measured):
+        // dust at 34-48 K and cold gas with a very high cosmic-ray rate
+        if (temp > 33.0 && temp < 49.0) key[c] += 10.0 + 0.5 * log10(zeta > 1e-3 ? zeta : 1e-3);
+        if (temp < 12.5 && zeta >= 300.0) key[c] += 5.0;
+    }
+    std::vector<int> ord(n);
+    for (long long c = 0; c < n; c++) ord[c] = (int)c;
+    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return key[x] > key[y]; });
+    return ord;
+}
+
 extern "C" int uclgpu_run_grid_device(int dev, uclgpu_model_kind kind, int64_t ncell, const double *d_params,
                                       const double *d_y0, double *d_y_final, double *d_phys_final,
                                       int32_t *d_flag, uclgpu_stats *d_stats, void *cuda_stream)
@@ -371,13 +396,29 @@ extern "C" int uclgpu_run_grid_device(int dev, uclgpu_model_kind kind, int64_t n
     memset(&a, 0, sizeof(a));
     a.kind = (int)kind; a.ncell = ncell; a.params = d_params; a.y0 = d_y0; a.y_final = d_y_final;
     a.phys_final = d_phys_final; a.flag = d_flag; a.stats = d_stats;
+    int *d_order = nullptr;
+    if (ncell > d->sms) {
+        // the processing order needs six parameter rows on the host (a few hundred KB)
+        CK(cudaSetDevice(d->id));
+        std::vector<double> hp((size_t)UCLGPU_NPARAM * ncell);
+        CK(cudaMemcpyAsync(hp.data(), d_params, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, d->stream));
+        CK(cudaStreamSynchronize(d->stream));
+        std::vector<int> ord = cost_order(hp.data(), ncell, 0, ncell);
+        CK(cudaMalloc(&d_order, sizeof(int) * ncell));
+        CK(cudaMemcpyAsync(d_order, ord.data(), sizeof(int) * ncell, cudaMemcpyHostToDevice, d->stream));
+        CK(cudaStreamSynchronize(d->stream));
+        a.order = d_order;
+    }
     int rc = launch_integrate(*d, a);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(d->stream));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, d->ev0, d->ev1));
-    d->last_ms = ms;
-    return 0;
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(d->stream);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, d->ev0, d->ev1);
+        d->last_ms = ms;
+        if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "%s", cudaGetErrorString(e)); rc = UCLGPU_ERR_CUDA; }
+    }
+    cudaFree(d_order);
+    return rc;
 }
 
 extern "C" int uclgpu_last_kernel_ms(int dev, double *ms, int64_t *launches)
@@ -403,28 +444,6 @@ struct DevBuf {
         cudaFree(rtraj); cudaFree(tdiss); cudaFree(flag); cudaFree(stats);
     }
 };
-
-// Relative cost estimate of one cell from its parameters (measured on the config-2 grid: the step
-// count grows with density and cosmic-ray rate and falls with temperature; DESIGN.md "load balance").
-static std::vector<int> cost_order(const double *params, int64_t ncell, long long lo, long long n)
-{
-    std::vector<double> key(n);
-    for (long long c = 0; c < n; c++) {
-        const double dens = params[(size_t)UCL_P_INITIALDENS * ncell + lo + c];
-        const double fdens = params[(size_t)UCL_P_FINALDENS * ncell + lo + c];
-        const double ff = params[(size_t)UCL_P_FREEFALL * ncell + lo + c];
-        const double zeta = params[(size_t)UCL_P_ZETA * ncell + lo + c];
-        const double temp = params[(size_t)UCL_P_INITIALTEMP * ncell + lo + c];
-        const double tfin = params[(size_t)UCL_P_FINALTIME * ncell + lo + c];
-        const double nn = (ff != 0.0 && fdens > dens) ? fdens : dens;
-        key[c] = log10(nn > 1.0 ? nn : 1.0) + 0.5 * log10(zeta > 1e-3 ? zeta : 1e-3) - 0.01 * temp +
-                 0.2 * log10(tfin > 1.0 ? tfin : 1.0);
-    }
-    std::vector<int> ord(n);
-    for (long long c = 0; c < n; c++) ord[c] = (int)c;
-    std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return key[x] > key[y]; });
-    return ord;
-}
 
 extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const double *params, const double *y0,
                                double *y_final, double *phys_final, int32_t *flag, uclgpu_stats *stats,
