@@ -263,12 +263,29 @@ __device__ __forceinline__ void nr_spline_small(const double *x, const double *y
     for (int k = n - 2; k >= 0; k--) y2[k] = y2[k] * y2[k + 1] + u[k];
 }
 
-// COPhotoDissRate photoreactions.f90:57-72,251-304 -- executed by ONE thread (cheap; it overlaps
-// with the plain flux phase of the other warps).
+// splint on a unit-spaced grid xa[k] = x0 + k (k = 0..n-1): same bracket rule and arithmetic as
+// nr_splint, with the abscissae computed instead of loaded (they are exact small integers)
+__device__ __forceinline__ double nr_splint_unit(double x0, const double *ya, const double *y2a, int n, double x)
+{
+    int jlo = 0;
+    for (int k = 0; k < n; k++) jlo += (x > x0 + (double)k) ? 1 : 0; // = the bisection result on a sorted grid
+    int jhi = jlo + 1;
+    if (jlo == 0) { jlo = 1; jhi = 2; }
+    if (jlo == n) { jlo = n - 1; jhi = n; }
+    double xlo = x0 + (double)(jlo - 1), xhi = x0 + (double)(jhi - 1);
+    double h = xhi - xlo;
+    double a = (xhi - x) / h;
+    double bb = (x - xlo) / h;
+    return a * ya[jlo - 1] + bb * ya[jhi - 1] +
+           ((a * a * a - a) * y2a[jlo - 1] + (bb * bb * bb - bb) * y2a[jhi - 1]) * (h * h) / 6.0;
+}
+
+// COPhotoDissRate photoreactions.f90:57-72,251-304 -- executed by ONE thread, on the critical path
+// of every RHS evaluation (the other warps wait for it at the barrier after the plain flux phase):
+// the shielding tables are in constant memory and both grids (log N(CO) = 12..18, log N(H2) = 18..23)
+// are unit spaced, so no table walk touches L2 or local memory.
 __device__ __noinline__ double co_photo_rate_dev(double nh2, double nco, double radfield, double av)
 {
-    const double nco_grid[7] = {12.0, 13.0, 14.0, 15.0, 16.0, 17.0, 18.0};
-    const double nh2_grid[6] = {18.0, 19.0, 20.0, 21.0, 22.0, 23.0};
     double lognco = log10(nco + 1.0), lognh2 = log10(nh2 + 1.0);
     double lu = log10(fabs(nco) + 1.0), lw = log10(fabs(nh2) + 1.0);
     if (lognco < 12.0) lognco = 12.0;
@@ -276,9 +293,44 @@ __device__ __noinline__ double co_photo_rate_dev(double nh2, double nco, double 
     if (lognco > 18.0) lognco = 18.0;
     if (lognh2 > 23.0) lognh2 = 23.0;
     double yy[7], y2[7];
-    for (int j = 0; j < 7; j++) yy[j] = nr_splint(nh2_grid, net_sco_rows + 6 * j, net_sco_d2 + 6 * j, 6, lognh2);
-    nr_spline_small(nco_grid, yy, 7, y2);
-    double ssf = pow(10.0, nr_splint(nco_grid, yy, y2, 7, lognco));
+#pragma unroll
+    for (int j = 0; j < 7; j++) yy[j] = nr_splint_unit(18.0, net_sco_rows + 6 * j, net_sco_d2 + 6 * j, 6, lognh2);
+    // natural spline over the unit-spaced N(CO) grid (nr_spline_small with x[i] = 12 + i)
+    {
+        double u[7];
+        y2[0] = 0.0;
+        u[0] = 0.0;
+#pragma unroll
+        for (int i = 1; i < 6; i++) {
+            const double xm = 12.0 + (double)(i - 1), x0 = 12.0 + (double)i, xp = 12.0 + (double)(i + 1);
+            double sig = (x0 - xm) / (xp - xm);
+            double p = sig * y2[i - 1] + 2.0;
+            y2[i] = (sig - 1.0) / p;
+            u[i] = (6.0 * ((yy[i + 1] - yy[i]) / (xp - x0) - (yy[i] - yy[i - 1]) / (x0 - xm)) / (xp - xm) - sig * u[i - 1]) / p;
+        }
+        y2[6] = (0.0 - 0.0 * u[5]) / (0.0 * y2[5] + 1.0);
+#pragma unroll
+        for (int k = 5; k >= 0; k--) y2[k] = y2[k] * y2[k + 1] + u[k];
+    }
+    // splint over N(CO): bracket computed, operands selected from registers
+    double ssf;
+    {
+        int jlo = 0;
+#pragma unroll
+        for (int k = 0; k < 7; k++) jlo += (lognco > 12.0 + (double)k) ? 1 : 0;
+        int jhi = jlo + 1;
+        if (jlo == 0) { jlo = 1; jhi = 2; }
+        if (jlo == 7) { jlo = 6; jhi = 7; }
+        double ylo = yy[0], yhi = yy[1], dlo = y2[0], dhi = y2[1];
+#pragma unroll
+        for (int k = 1; k < 6; k++)
+            if (jlo - 1 == k) { ylo = yy[k]; yhi = yy[k + 1]; dlo = y2[k]; dhi = y2[k + 1]; }
+        double xlo = 12.0 + (double)(jlo - 1), xhi = 12.0 + (double)(jhi - 1);
+        double h = xhi - xlo;
+        double a = (xhi - lognco) / h;
+        double bb = (lognco - xlo) / h;
+        ssf = pow(10.0, a * ylo + bb * yhi + ((a * a * a - a) * dlo + (bb * bb * bb - bb) * dhi) * (h * h) / 6.0);
+    }
     double lb = (5675.0 - 200.6 * lw) - (571.6 - 24.09 * lw) * lu + (18.22 - 0.7664 * lw) * (lu * lu);
     if (lb > 1076.1) lb = 1076.1;
     if (lb < 913.6) lb = 913.6;

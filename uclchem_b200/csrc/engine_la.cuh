@@ -11,38 +11,93 @@
 // desc[slot] = {term_begin, target | nterms<<16 | log2(team)<<28}; teams are aligned
 // power-of-two groups of consecutive slots; lane l of a team sums terms l, l+T, ...
 // A program is a list of units (one pass of NT slots of one level; units[k] = {first slot,
-// end slot | barrier-after << 31}); levels are separated by block barriers.  A warp whose
-// 32 slots lie beyond the unit's end goes straight to the barrier: most solve levels only
-// occupy a few warps, and issue slots -- not bandwidth -- are what these phases cost.
-// Terms are fetched in one batch of U independent loads per lane.
-template <int U, class TermT, class TermF, class FinF>
+// end slot | barrier-after << 31}, in constant memory); levels are separated by block
+// barriers.  A warp whose 32 slots lie beyond the unit's end goes straight to the barrier:
+// most solve levels only occupy a few warps, and issue slots -- not bandwidth -- are what
+// these phases cost.
+//
+// The tables live in L2 (the shared-memory carve-out leaves only ~28 KB of L1), and a level is
+// a dependent chain descriptor -> terms -> shared-memory operands.  None of the table reads
+// depends on numeric data, so the executor runs ahead of the level barriers: the descriptor (and
+// the optional per-target `pre` word) of unit k+1 is loaded into registers while unit k computes,
+// and the term lines of unit k+1 are pulled into L1 with prefetch instructions before the barrier
+// of unit k.  Device functions only get ~60 registers here (the call chain shares the 128 of a
+// 512-thread CTA), so the terms themselves are not held in registers across the barrier.
+struct TeamSlot {
+    uint2 d;       // descriptor
+    uint32_t sl;   // slot index
+    uint32_t aux;  // pre(target)
+    bool warp_on;  // this warp has slots in the unit (warp-uniform)
+};
+
+// acc = p ? fma(a, x, acc) : acc as one predicated DFMA (keeps the select off the dependent chain)
+__device__ __forceinline__ double masked_fma(double a, double x, double acc, bool p)
+{
+    asm("{ .reg .pred q; setp.ne.u32 q, %3, 0; @q fma.rn.f64 %0, %1, %2, %0; }" : "+d"(acc) : "d"(a), "d"(x), "r"((uint32_t)p));
+    return acc;
+}
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <int U, class TermT, class TermF, class PreF, class FinF>
 __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, const TermT *__restrict__ terms,
-                                           const uint32_t *__restrict__ units, int nunits, TermF term, FinF fin)
+                                           const uint32_t *units, int nunits, TermF term, PreF pre, FinF fin)
 {
     const uint2 *d2 = reinterpret_cast<const uint2 *>(desc);
     const uint2 *units2 = reinterpret_cast<const uint2 *>(units);
+    const uint32_t lane = threadIdx.x & 31u;
+    constexpr uint32_t PER_LINE = 128u / sizeof(TermT);
+    auto fetch_desc = [&](int k) {
+        TeamSlot t;
+        t.d = make_uint2(0u, 0xFFFFu);
+        t.sl = 0u;
+        t.aux = 0u;
+        t.warp_on = false;
+        if (k < nunits) {
+            const uint2 un = units2[k];
+            t.sl = un.x + threadIdx.x;
+            t.warp_on = t.sl - lane < (un.y & 0x7FFFFFFFu); // slot ranges are padded to multiples of 32
+            if (t.warp_on) t.d = __ldg(d2 + t.sl);
+        }
+        return t;
+    };
+    // second half of the look-ahead (needs the descriptor to have arrived): term lines -> L1, pre word
+    auto look_ahead = [&](TeamSlot &t) {
+        const uint32_t target = t.d.y & 0xFFFFu, n = (t.d.y >> 16) & 0xFFFu;
+        const uint32_t T = 1u << ((t.d.y >> 28) & 7u), lit = t.sl & (T - 1u);
+        if (target != 0xFFFFu) {
+            const TermT *tp = terms + t.d.x;
+            if (lit * PER_LINE < n) prefetch_l1(tp + lit * PER_LINE);
+            if (lit == 0u) {
+                prefetch_l1(tp + n - 1u);
+                t.aux = pre(target);
+            }
+        }
+    };
+    TeamSlot cur = fetch_desc(0);
+    look_ahead(cur);
     for (int k = 0; k < nunits; k++) {
-        const uint2 un = __ldg(units2 + k);
-        const uint32_t end = un.y & 0x7FFFFFFFu;
-        const uint32_t sl = un.x + threadIdx.x;
-        if (sl - (threadIdx.x & 31u) < end) { // warp-uniform
-            const uint2 d = __ldg(d2 + sl);   // slot ranges are padded to multiples of 32
-            const uint32_t target = d.y & 0xFFFFu, n = (d.y >> 16) & 0xFFFu;
-            const int tl = (int)((d.y >> 28) & 7u);
-            const uint32_t T = 1u << tl, lane_in_team = sl & (T - 1u);
+        TeamSlot nxt = fetch_desc(k + 1); // in flight while unit k computes
+        if (cur.warp_on) {
+            const uint32_t target = cur.d.y & 0xFFFFu, n = (cur.d.y >> 16) & 0xFFFu;
+            const int tl = (int)((cur.d.y >> 28) & 7u);
+            const uint32_t T = 1u << tl, lit = cur.sl & (T - 1u);
             double acc = 0.0;
             if (target != 0xFFFFu) {
-                const TermT *tp = terms + d.x;
-                for (uint32_t q0 = lane_in_team; q0 < n; q0 += T * U) {
+                // branch-free batch: U unconditional table loads (the generator pads every term table
+                // by 32*U entries, and whatever follows a row are valid terms of other rows), then all
+                // shared-memory operand loads, then one chain of masked FMAs in term order
+                const TermT *tp = terms + cur.d.x + lit;
+                for (uint32_t q0 = lit; q0 < n; q0 += T * U, tp += T * U) {
                     TermT tb[U];
 #pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        uint32_t q = q0 + (uint32_t)u * T;
-                        if (q < n) tb[u] = __ldg(tp + q);
-                    }
+                    for (int u = 0; u < U; u++) tb[u] = __ldg(tp + (uint32_t)u * T);
+                    double2 ax[U];
 #pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (q0 + (uint32_t)u * T < n) acc += term(tb[u]);
+                    for (int u = 0; u < U; u++) ax[u] = term(tb[u]);
+                    asm volatile("" ::: "memory"); // issue every operand load before the dependent FMA chain
+#pragma unroll
+                    for (int u = 0; u < U; u++) acc = masked_fma(ax[u].x, ax[u].y, acc, q0 + (uint32_t)u * T < n);
                 }
             }
             const int tmax = __reduce_max_sync(0xffffffffu, tl);
@@ -50,9 +105,11 @@ __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, co
                 double v = __shfl_xor_sync(0xffffffffu, acc, o);
                 if ((uint32_t)o < T) acc += v;
             }
-            if (target != 0xFFFFu && lane_in_team == 0) fin(target, acc);
+            if (target != 0xFFFFu && lit == 0u) fin(target, acc, cur.aux);
         }
-        if (un.y >> 31) BLOCK_SYNC();
+        look_ahead(nxt);
+        if (units2[k].y >> 31) BLOCK_SYNC();
+        cur = nxt;
     }
 }
 
@@ -128,11 +185,9 @@ __device__ __noinline__ void rhs_eval(Smem &s, double *ydot)
         const double *flux = s.flux;
         run_levels<8>(
             net_gather_desc, net_gather_terms, net_gather_units, NET_GATHER_NUNITS,
-            [&](uint16_t t) {
-                double v = flux[t & 0x7FFFu];
-                return (t & 0x8000u) ? -v : v;
-            },
-            [&](uint32_t target, double acc) { ydot[target] = acc; });
+            [&](uint16_t t) { return make_double2(flux[t & 0x7FFFu], (t & 0x8000u) ? -1.0 : 1.0); },
+            [](uint32_t) { return 0u; },
+            [&](uint32_t target, double acc, uint32_t) { ydot[target] = acc; });
     }
     // ---- three-phase transfer odes.f90:4815-5180 ------------------------------------------------
     {
@@ -203,9 +258,10 @@ __device__ __noinline__ void jac_eval(Smem &s)
                 uint32_t kind = (t.x >> 28) & 7u;
                 if (kind == 1u) v *= dblr;
                 else if (kind == 2u) v *= dism;
-                return (t.x >> 31) ? -v : v;
+                return make_double2(v, (t.x >> 31) ? -1.0 : 1.0);
             },
-            [&](uint32_t target, double acc) { val[target] = acc; });
+            [](uint32_t) { return 0u; },
+            [&](uint32_t target, double acc, uint32_t) { val[target] = acc; });
     }
     {
         // tau row and three-phase transfer terms (each position has exactly one writer)
@@ -390,10 +446,10 @@ __device__ __noinline__ bool factor_p(Smem &s, Blk &b)
     TIMER_START
     run_levels<8>(
         net_factor_desc, net_factor_terms, net_factor_units, NET_FACTOR_NUNITS,
-        [&](uint32_t t) { return val[t >> 16] * val[t & 0xFFFFu]; },
-        [&](uint32_t target, double acc) {
+        [&](uint32_t t) { return make_double2(val[t >> 16], val[t & 0xFFFFu]); },
+        [](uint32_t target) { return (uint32_t)__ldg(net_factor_diag + target); },
+        [&](uint32_t target, double acc, uint32_t d) {
             double x = val[target] - acc;
-            uint32_t d = net_factor_diag[target];
             if (d == 0xFFFEu) x = 1.0 / x;       // sparse pivot: keep the reciprocal
             else if (d != 0xFFFFu) x *= val[d];  // L entry: scale by 1/pivot
             val[target] = x;
@@ -421,8 +477,9 @@ __device__ __noinline__ void lin_solve(Smem &s)
     // forward substitution through the sparse rows, then b_T -= L21 x (one program: fwd levels + tail)
     run_levels<8>(
         net_fwd_desc, net_fwd_terms, net_fwd_units, NET_FWD_NUNITS,
-        [&](uint32_t t) { return val[t >> 16] * xs[t & 0xFFFFu]; },
-        [&](uint32_t target, double acc) { xs[target] -= acc; });
+        [&](uint32_t t) { return make_double2(val[t >> 16], xs[t & 0xFFFFu]); },
+        [](uint32_t) { return 0u; },
+        [&](uint32_t target, double acc, uint32_t) { xs[target] -= acc; });
     {
         // x_T = Tinv * b_T : 4 lanes per row
         const double *T = val + NET_OFF_DENSE;
@@ -441,7 +498,8 @@ __device__ __noinline__ void lin_solve(Smem &s)
     BLOCK_SYNC();
     run_levels<8>(
         net_bwd_desc, net_bwd_terms, net_bwd_units, NET_BWD_NUNITS,
-        [&](uint32_t t) { return val[t >> 16] * xs[t & 0xFFFFu]; },
-        [&](uint32_t target, double acc) { xs[target] = (xs[target] - acc) * s.invd[target]; });
+        [&](uint32_t t) { return make_double2(val[t >> 16], xs[t & 0xFFFFu]); },
+        [](uint32_t) { return 0u; },
+        [&](uint32_t target, double acc, uint32_t) { xs[target] = (xs[target] - acc) * s.invd[target]; });
     TIMER_ADD(cyc_solve)
 }

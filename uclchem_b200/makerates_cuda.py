@@ -36,6 +36,7 @@ from .network import N_EXT, TYPE_ID, TYPE_NAMES, Network
 
 NTHREADS = 512
 NULL_TARGET = 0xFFFF
+TERM_PAD = 256  # >= 32 lanes x 8 terms per batch
 
 
 # --------------------------------------------------------------------------
@@ -356,7 +357,7 @@ def photo_tables() -> dict:
 # --------------------------------------------------------------------------
 # emission
 # --------------------------------------------------------------------------
-def _c_array(name, arr, ctype, per_line=16):
+def _c_array(name, arr, ctype, per_line=16, qual="__device__"):
     arr = np.asarray(arr).ravel()
     if ctype == "double":
         body = [repr(float(v)) if np.isfinite(v) else "0.0" for v in arr]
@@ -368,7 +369,7 @@ def _c_array(name, arr, ctype, per_line=16):
     n = max(1, len(arr))
     if len(arr) == 0:
         lines = ["0"]
-    return f"__device__ __align__(16) const {ctype} {name}[{n}] = {{\n  " + ",\n  ".join(lines) + "\n};\n"
+    return f"{qual} __align__(16) const {ctype} {name}[{n}] = {{\n  " + ",\n  ".join(lines) + "\n};\n"
 
 
 def emit(gen: Generated, outdir: Path, tag: str) -> Path:
@@ -438,11 +439,12 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     w(_c_array("net_mass1", rt["mass1"], "double"))
     w(_c_array("net_freeze_partners", net.freeze_partners, "int16_t"))
     w(_c_array("net_gar_params", net.gar_params, "double"))
-    w(_c_array("net_lambda_grid", ph["lambda_grid"], "double"))
-    w(_c_array("net_xlambda_grid", ph["xlambda_grid"], "double"))
-    w(_c_array("net_xlambda_d2", ph["xlambda_d2"], "double"))
-    w(_c_array("net_sco_rows", ph["sco_rows"], "double"))
-    w(_c_array("net_sco_d2", ph["sco_d2"], "double"))
+    # photo-rate tables are walked by a single lane per RHS evaluation (a latency chain): constant memory
+    w(_c_array("net_lambda_grid", ph["lambda_grid"], "double", qual="__constant__"))
+    w(_c_array("net_xlambda_grid", ph["xlambda_grid"], "double", qual="__constant__"))
+    w(_c_array("net_xlambda_d2", ph["xlambda_d2"], "double", qual="__constant__"))
+    w(_c_array("net_sco_rows", ph["sco_rows"], "double", qual="__constant__"))
+    w(_c_array("net_sco_d2", ph["sco_d2"], "double", qual="__constant__"))
     w("\n// ---- RHS: flux table + gather program ---------------------------------------------\n")
     w(f"#define NET_NPLAIN {gen.n_plain}\n")
     w(_c_array("net_flux_tab", gen.flux_tab, "uint32_t"))
@@ -477,6 +479,9 @@ def _emit_program(w, name, programs, term16=False, term64=False):
         terms.extend(p.terms.tolist())
         lv.append(lv[-1] + p.nslots)
     desc = np.concatenate(desc) if desc else np.zeros((0, 2), np.uint32)
+    # the device executor loads term batches unconditionally (lane + u*team, u < 8) and masks the
+    # sum: pad so that the last row's batch stays inside the table (index 0 is valid everywhere)
+    terms.extend([0] * TERM_PAD)
     w(f"#define {name.upper()}_NLEVELS {len(programs)}\n")
     w(_c_array(name + "_desc", desc, "uint32_t"))
     if term16:
@@ -500,7 +505,8 @@ def _emit_program(w, name, programs, term16=False, term64=False):
         for i, st in enumerate(starts):
             units.append((st, e0 | ((1 << 31) if i == len(starts) - 1 else 0)))
     w(f"#define {name.upper()}_NUNITS {len(units)}\n")
-    w(_c_array(name + "_units", np.asarray(units, dtype=np.uint64).ravel(), "uint32_t"))
+    # unit tables are read with a block-uniform index: constant memory (no L2 round trip per level)
+    w(_c_array(name + "_units", np.asarray(units, dtype=np.uint64).ravel(), "uint32_t", qual="__constant__"))
 
 
 def main(argv=None):
