@@ -104,12 +104,29 @@ def cpu_cores():
         return os.cpu_count() or 1
 
 
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def bounded_cells(ncell):
+    """Cells a bounded CPU sample may draw from.  1.6 % of the config-2 grid are cells where DVODE
+    itself stalls (MXSTEP hit inside single output intervals: 1e5-1e6 steps, minutes to tens of minutes
+    of CPU time each -- DESIGN.md section 6).  Their indices were measured on the GPU in round 1 and are
+    committed as tools/config2_heavy_cells.npy; leaving them out bounds the sample and makes the CPU
+    figure an UPPER bound of the CPU's whole-grid rate (the GPU legs integrate every cell)."""
+    ok = np.ones(ncell, bool)
+    f = ROOT / "tools" / "config2_heavy_cells.npy"
+    if ncell == 10000 and f.exists():
+        ok[np.load(f)] = False
+    return np.where(ok)[0]
+
+
 def run_oracle_sample(params, cores, offset=0):
-    """Time the CPU restatement on `cores` evenly spaced cells of the workload, one per core."""
+    """Time the CPU restatement on `cores` evenly spaced (bounded) cells of the workload, one per core."""
     from oracle.oracle import Oracle
     from uclchem_b200.network import load_default
-    ncell = params.shape[1]
-    idx = (np.linspace(0, ncell - 1, cores).astype(int) + offset) % ncell
+    pool = bounded_cells(params.shape[1])
+    idx = pool[(np.linspace(0, len(pool) - 1, cores).astype(int) + offset) % len(pool)]
     orc = Oracle(load_default())
     t0 = time.perf_counter()
     y, _, flag, _ = orc.run_grid(0, np.ascontiguousarray(params[:, idx]), nthreads=cores)
@@ -132,9 +149,14 @@ def main():
     if a.cells:
         params = np.ascontiguousarray(params[:, np.linspace(0, params.shape[1] - 1, a.cells).astype(int)])
     ncell = params.shape[1]
+    # warm-up steps run the same kernel over a bounded stride of the same grid (clocks, instruction
+    # cache, lazy module load); a full pass is tens of seconds and has no state a warm-up could prime
+    n_warm = min(ncell, 592)
+    warm_idx = np.linspace(0, ncell - 1, n_warm).astype(int)
     workload = {"workload": f"config[1]: {ncell}-point static cloud grid (25 n_H x 20 T x 20 zeta), 1 Myr, default "
                             "network 335 species / 3203 reactions, reltol 1e-8", "cells_per_gpu": ncell,
-                "timing": "L2 flushed (256 MiB write) between timed steps"}
+                "timing": "L2 flushed (256 MiB write) between timed steps",
+                "warmup_step": f"one pass over a {n_warm}-cell stride of the same grid (same kernel and launch shape)"}
 
     # ------------------------------------------------------------------ reference arm
     if a.impl == "reference":
@@ -150,7 +172,8 @@ def main():
             n += len(idx)
         dt = time.perf_counter() - t0
         v = n / dt
-        sample = f"{cores} evenly spaced cells of the grid per step, one per host core"
+        sample = (f"{cores} evenly spaced cells of the grid per step, one per host core; the 1.6 % of cells where "
+                  "DVODE stalls (tools/config2_heavy_cells.npy) are excluded, so this is an upper bound of the CPU rate")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
@@ -225,16 +248,22 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t[0].item(), t[1].item(), launches
 
+    d_wparams = torch.from_numpy(np.ascontiguousarray(params[:, warm_idx])).to(dev)
     for _ in range(a.warmup):
-        step_device()
+        lib._check(lib.lib.uclgpu_run_grid_device(local_rank, 0, n_warm, d_wparams.data_ptr(), None, d_y.data_ptr(),
+                                                  d_phys.data_ptr(), d_flag.data_ptr(), d_stats.data_ptr(), None))
+        flush.fill_(1)
+    log(f"warm-up done ({a.warmup} x {n_warm} cells); timing {a.steps} device-resident pass(es) over {ncell} cells")
     with ClockSampler(local_rank) as clk:
         dt, kernel_ms, launches = timed(step_device, a.steps)
+    log(f"device-resident leg: {dt:.1f} s ({world * ncell * a.steps / dt:.1f} models/s); timing the e2e leg")
     clocks = clk.summary()
     value = world * ncell * a.steps / dt
     stats = d_stats.cpu().numpy()
     flags = d_flag.cpu().numpy()
     dt_e2e, _, launches_e2e = timed(step_e2e, a.steps)
     e2e_value = world * ncell * a.steps / dt_e2e
+    log(f"e2e leg: {dt_e2e:.1f} s ({e2e_value:.1f} models/s)")
     assert np.array_equal(h_flag.numpy(), flags)
 
     if rank == 0:
@@ -258,7 +287,9 @@ def main():
                 "frac": w_flop / kern_s / 1e12 / pk.value if pk.value else None,
                 "peak_source": "DFMA micro-benchmark run by this process (uclgpu_fp64_peak)"}
         cores = cpu_cores()
+        log(f"cpu_baseline: oracle on {cores} cores")
         cv, cdt, idx, yref, cflag = run_oracle_sample(params, cores)
+        log(f"cpu_baseline: {cdt:.1f} s")
         y_gpu = h_y.numpy()[idx][:, :335]
         m = yref[:, :335] > 1e-15
         dex = float(np.abs(np.log10(y_gpu[m] / yref[:, :335][m])).max())
@@ -272,7 +303,9 @@ def main():
             "gpu_launches": int(launches + launches_e2e),
             "roofline": roof, "fp64": fp64,
             "cpu_baseline": {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(idx)} evenly spaced cells of the grid, one per host core, {cdt:.1f} s"},
+                             "sample": f"{len(idx)} evenly spaced cells of the grid, one per host core, {cdt:.1f} s; the "
+                                       "1.6 % of cells where DVODE stalls (tools/config2_heavy_cells.npy) are "
+                                       "excluded: an upper bound of the CPU's whole-grid rate"},
             "parity": {"max_dex_vs_oracle_on_sample": dex, "flags_nonzero": int((flags != 0).sum()),
                        "oracle_flags_nonzero": int((cflag != 0).sum())},
             "solver": {"steps_per_model": S["nst"] / ncell, "lu_per_model": S["nlu"] / ncell,

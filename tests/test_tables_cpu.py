@@ -47,6 +47,14 @@ def test_gather_program_matches_csr(gen, eng):
     out = np.zeros(sym.neq)
     gen.gather.run(lambda t: -flux[t & 0x7FFF] if (t >> 15) & 1 else flux[t & 0x7FFF],
                    lambda tg, s: out.__setitem__(tg, s))
+    # the two state-dependent photo reactions are not in the gather program: the RHS adds them afterwards
+    assert sorted(gen.deferred) == sorted(int(net_r) for net_r in (gen.net.reaction_idx["nR_H2_hv"],
+                                                                    gen.net.reaction_idx["nR_CO_hv"]))
+    assert not set(gen.deferred) & set(int(r) for r in gen.flux_order)
+    assert len(gen.flux_order) == gen.net.nreac - 2
+    for r in gen.deferred:
+        for i, sg in gen.deferred_rows[r]:
+            out[i] += sg * flux[r]
     rows = np.repeat(np.arange(335), np.diff(sym.g_ptr))
     ref = np.bincount(rows, weights=flux[sym.g_reac] * sym.g_sign, minlength=335)
     assert np.abs(out[:335] - ref).max() <= 1e-14 * np.abs(ref).max()

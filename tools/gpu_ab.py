@@ -10,7 +10,7 @@ from uclchem_b200._capi import Library, STAT_FIELDS
 from uclchem_b200.params import PARAM_INDEX
 P = config2_params()
 n = int(sys.argv[3]); final = float(sys.argv[4]) if len(sys.argv) > 4 else 1e6
-heavy = set(np.load(ROOT / "tools/heavy_cells.npy").tolist())
+heavy = set(np.load(ROOT / "tools/config2_heavy_cells.npy").tolist())
 idx = [i for i in np.linspace(0, P.shape[1] - 1, n).astype(int) if i not in heavy]
 p = np.ascontiguousarray(P[:, idx]); p[PARAM_INDEX["finaltime"]] = final
 res = {}

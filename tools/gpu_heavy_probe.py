@@ -1,4 +1,4 @@
-"""Run the cells of config 2 that exceeded a 30000-step budget (tools/heavy_cells.npy) with a larger budget."""
+"""Run the cells of config 2 that exceeded a 30000-step budget (tools/config2_heavy_cells.npy) with a larger budget."""
 import sys, time, functools
 from pathlib import Path
 ROOT = Path(__file__).resolve().parents[1]; sys.path.insert(0, str(ROOT))
@@ -9,7 +9,7 @@ from uclchem_b200._capi import get_library, STAT_FIELDS
 from uclchem_b200.params import PARAM_INDEX
 lib = get_library(); lib.init()
 P = config2_params()
-idx = np.load(ROOT / "tools/heavy_cells.npy")
+idx = np.load(ROOT / "tools/config2_heavy_cells.npy")
 budget = int(sys.argv[1])
 p = np.ascontiguousarray(P[:, idx])
 t = time.time(); o = lib.run_grid(0, p, step_budget=budget); dt = time.time() - t

@@ -154,7 +154,9 @@ __device__ __noinline__ void vjust_dev(Smem &s, int iord)
     BLOCK_SYNC();
 }
 
-// Pascal-triangle predict / retract, dvode.f90:7367-7375 / :7396-7402 (per equation, no barrier)
+// Pascal-triangle predict / retract, dvode.f90:7367-7375 / :7396-7402 (per equation, no barrier).
+// Fully unrolled over the maximum order with predicates so the column stays in registers (a
+// dynamically indexed local array would live in local memory, i.e. behind the ~28 KB L1).
 __device__ __forceinline__ void predict_dev(Smem &s, int nq, int sign)
 {
     const int i = threadIdx.x;
@@ -162,14 +164,114 @@ __device__ __forceinline__ void predict_dev(Smem &s, int nq, int sign)
         double c[LMAXORD];
 #pragma unroll
         for (int j = 0; j < LMAXORD; j++) c[j] = s.yh[j][i];
-        for (int jb = 1; jb <= nq; jb++)
-            for (int j = nq - jb; j < nq; j++) {
-                // j runs over columns (0-based) I1..NQ-1 in increasing order
-                if (sign > 0) c[j] += c[j + 1]; else c[j] -= c[j + 1];
+#pragma unroll
+        for (int jb = 1; jb <= LMAXORD - 1; jb++) {
+            if (jb <= nq) {
+#pragma unroll
+                for (int j = 0; j < LMAXORD - 1; j++) {
+                    // j runs over columns (0-based) NQ-JB..NQ-1 in increasing order
+                    if (j >= nq - jb && j < nq) c[j] = (sign > 0) ? c[j] + c[j + 1] : c[j] - c[j + 1];
+                }
             }
+        }
 #pragma unroll
         for (int j = 0; j < LMAXORD; j++) s.yh[j][i] = c[j];
     }
+}
+
+// ---- scalar sections (thread 0 only) -------------------------------------------------------
+// DVODE's control logic is sequential scalar code between vector operations.  Every scalar
+// section costs two block barriers plus a chain of dependent shared-memory accesses on one
+// thread while 511 wait, so the sections of the common path are fused: one section before the
+// corrector (step_head_scalar) and one after it (post_converge_scalar).  The statements and
+// their order are DVODE's; only the barriers between them are gone.
+
+// label 60 (rescale) + label 70 (advance, DVSET) of DVSTEP, head of DVNLSD, label 10 of DVNLSD
+__device__ __forceinline__ void step_head_scalar(Scalars &st, int do_rescale)
+{
+    if (do_rescale) {
+        st.h = st.hscal * st.eta;
+        st.hscal = st.h;
+        st.rc = st.rc * st.eta;
+    }
+    st.tn += st.h;
+    vset_dev(st);
+    st.rl1 = 1.0 / st.el[2];
+    st.rc = st.rc * (st.rl1 / st.prl1);
+    st.prl1 = st.rl1;
+    // head of DVNLSD
+    if (st.jstart == 0) st.nslp = 0;
+    if (st.nflag == 0) st.icf = 0;
+    if (st.nflag == -2) st.ipup = 1;
+    if (st.jstart == 0) st.ipup = 1;
+    st.drc = fabs(st.rc - 1.0);
+    if (st.drc > V_CCMAX || st.nst_call >= st.nslp + V_MSBP) st.ipup = 1;
+    // label 10 of DVNLSD
+    st.m_iter = 0;
+    st.delp = 0.0;
+    st.nfe++;
+}
+
+// Everything DVODE does with scalars once the corrector has converged with ACNRM = acn:
+// end of DVNLSD, the local error test (label 80), the bookkeeping of a successful step
+// (dvode.f90:7417-7468), the step-size selection when no order change is up for decision
+// (label 130 with NQWAIT != 0) and label 250.  st.fz_level tells the block how far it got:
+//   1 error test failed | 2 step accepted, order selection (needs two more norms) pending |
+//   3 step accepted and fully booked (JSTART = 1 included)
+__device__ __forceinline__ void post_converge_scalar(Scalars &st, double acn)
+{
+    st.acnrm = acn;
+    st.nflag = 0;
+    st.jcur = 0;
+    st.icf = 0;
+    st.dsm = st.acnrm / st.tq[2];
+    if (!(st.dsm <= 1.0)) {
+        st.fz_level = 1;
+        return;
+    }
+    st.kflag = 0;
+    st.nst++;
+    st.nst_call++;
+    st.hu = st.h;
+    st.nqu = st.nq;
+    for (int iback = 1; iback <= st.nq; iback++) {
+        int i = st.l - iback;
+        st.tau[i + 1] = st.tau[i];
+    }
+    st.tau[1] = st.h;
+    st.nqwait--;
+    st.fz_save = (st.l != st.lmax && st.nqwait == 1) ? 1 : 0; // save ACOR for the order-up estimate
+    if (st.fz_save) st.conp = st.tq[5];
+    const bool sel = fabs(st.etamax - 1.0) > 0.0;
+    if (sel && st.nqwait == 0) {
+        st.fz_level = 2;
+        return;
+    }
+    if (sel) {
+        double flotl = (double)st.l;
+        st.eta = 1.0 / (pow(V_BIAS2 * st.dsm, 1.0 / flotl) + V_ADDON);
+        st.newq = st.nq;
+        if (st.eta < V_THRESH || fabs(st.etamax - 1.0) <= 0.0) {
+            st.newq = st.nq;
+            st.newh = 0;
+            st.eta = 1.0;
+            st.hnew = st.h;
+        } else {
+            st.eta = fmin(st.eta, st.etamax);
+            st.newh = 1;
+            st.hnew = st.h * st.eta;
+        }
+    } else {
+        if (st.nqwait < 2) st.nqwait = 2;
+        st.newq = st.nq;
+        st.newh = 0;
+        st.eta = 1.0;
+        st.hnew = st.h;
+    }
+    st.etamax = V_ETAMX3;
+    if (st.nst_call <= 10) st.etamax = V_ETAMX2;
+    st.jstart = 1;
+    st.fz_level = 3;
 }
 
 // DVNLSD dvode.f90:7926.  On return st.nflag = 0 (converged, st.acnrm set) or -1.
@@ -178,12 +280,9 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
     Scalars &st = s.st;
     const int tid = threadIdx.x;
     for (;;) { // label 10
+        // (M = 0, DELP = 0, NFE++ of label 10 are part of the scalar section that precedes every entry)
         if (tid < NEQ) s.y[tid] = s.yh[0][tid];
-        T0_BEGIN
-        st.m_iter = 0;
-        st.delp = 0.0;
-        st.nfe++;
-        T0_END
+        BLOCK_SYNC();
         rhs_eval(s, s.savf);
         if (st.ipup > 0) { // block-uniform (published before the last barrier)
             // DVJAC dvode.f90:8200-8206: re-evaluate the Jacobian or reuse the saved copy
@@ -222,14 +321,7 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
         int outcome; // 1 converged, 2 diverged
         for (;;) {   // label 30/40
             BLOCK_SYNC();
-            if (tid < NAUG) {
-                int o = net_perm[tid];
-                double v = 0.0;
-                if (o < NEQ) v = (st.rl1 * st.h) * s.savf[o] - (st.rl1 * s.yh[1][o] + s.acor[o]);
-                s.xs[tid] = v;
-            }
-            BLOCK_SYNC();
-            constraint_rhs(s);
+            newton_rhs(s);
             const bool dump = b.trace && b.dump && b.trace_n == b.dump_at;
             if (dump) {
                 double *D = b.dump;
@@ -277,6 +369,8 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
             }
             if (dcon <= 1.0) {
                 st.flag = 1;
+                st.fz_level = 0;
+                if (st.m_iter == 0) post_converge_scalar(st, del); // ACNRM = DEL: nothing else to reduce
             } else {
                 st.m_iter++;
                 if (st.m_iter == V_MAXCOR || (st.m_iter >= 2 && del > V_RDIV * st.delp) || !isfinite(del)) {
@@ -295,14 +389,12 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
             rhs_eval(s, s.savf);
         }
         if (outcome == 1) {
-            double acn = st.del;
-            if (st.m_iter > 0) acn = wrms_norm(s, b, s.acor, s.ewt);
-            T0_BEGIN
-            st.acnrm = acn;
-            st.nflag = 0;
-            st.jcur = 0;
-            st.icf = 0;
-            T0_END
+            if (st.m_iter > 0) {
+                double acn = wrms_norm(s, b, s.acor, s.ewt);
+                T0_BEGIN
+                post_converge_scalar(st, acn);
+                T0_END
+            }
             return;
         }
         // label 60
@@ -310,6 +402,9 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
         T0_BEGIN
         st.icf = 1;
         st.ipup = 1;
+        st.m_iter = 0; // label 10
+        st.delp = 0.0;
+        st.nfe++;
         T0_END
     }
     // label 70
@@ -327,6 +422,7 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
     const int tid = threadIdx.x;
     int adj = 0;        // pending DVJUST (-1 / +1)
     int do_rescale = 0; // label 60 pending
+    int head_done = 0;  // step_head_scalar already ran in the previous scalar section
     T0_BEGIN
     st.told = st.tn;
     st.ncf = 0;
@@ -356,38 +452,33 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
         st.nqwait = 2;
         st.hscal = st.h;
     }
+    st.fz_head = 0;
+    if (st.flag == 0) { // no order change pending: go straight on to label 60/70
+        step_head_scalar(st, st.flag2);
+        st.fz_head = 1;
+    }
     T0_END
     adj = st.flag;
     do_rescale = st.flag2;
+    head_done = st.fz_head;
     if (adj != 0) {
         vjust_dev(s, adj);
         T0_BEGIN
         st.nq = st.newq;
         st.l = st.nq + 1;
         st.nqwait = st.l;
+        step_head_scalar(st, do_rescale);
         T0_END
+        head_done = 1;
     }
+    bool booked = false; // JSTART = 1 already set by a fused section
     for (;;) {
-        // label 60 (rescale) + label 70 (advance, DVSET) scalar part
-        T0_BEGIN
-        if (do_rescale) {
-            st.h = st.hscal * st.eta;
-            st.hscal = st.h;
-            st.rc = st.rc * st.eta;
+        if (!head_done) {
+            T0_BEGIN
+            step_head_scalar(st, do_rescale);
+            T0_END
         }
-        st.tn += st.h;
-        vset_dev(st);
-        st.rl1 = 1.0 / st.el[2];
-        st.rc = st.rc * (st.rl1 / st.prl1);
-        st.prl1 = st.rl1;
-        // head of DVNLSD
-        if (st.jstart == 0) st.nslp = 0;
-        if (st.nflag == 0) st.icf = 0;
-        if (st.nflag == -2) st.ipup = 1;
-        if (st.jstart == 0) st.ipup = 1;
-        st.drc = fabs(st.rc - 1.0);
-        if (st.drc > V_CCMAX || st.nst_call >= st.nslp + V_MSBP) st.ipup = 1;
-        T0_END
+        head_done = 0;
         if (tid < NEQ) {
             if (do_rescale) {
                 double r = 1.0;
@@ -421,67 +512,43 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
             do_rescale = 1;
             continue;
         }
-        // label 80: local error test
-        T0_BEGIN
-        st.dsm = st.acnrm / st.tq[2];
-        st.flag = (st.dsm <= 1.0) ? 1 : 0;
-        T0_END
-        if (st.flag) {
+        // label 80: the error test and the scalar bookkeeping ran in post_converge_scalar
+        const int lvl = st.fz_level;
+        if (lvl >= 2) {
             // ---- successful step: dvode.f90:7417-7468 ----
             if (tid < NEQ) {
                 double a = s.acor[tid];
                 for (int j = 1; j <= st.l; j++) s.yh[j - 1][tid] += st.el[j] * a;
+                if (st.fz_save) s.yh[st.lmax - 1][tid] = a;
             }
-            T0_BEGIN
-            st.kflag = 0;
-            st.nst++;
-            st.nst_call++;
-            st.hu = st.h;
-            st.nqu = st.nq;
-            for (int iback = 1; iback <= st.nq; iback++) {
-                int i = st.l - iback;
-                st.tau[i + 1] = st.tau[i];
-            }
-            st.tau[1] = st.h;
-            st.nqwait--;
-            st.flag = (st.l != st.lmax && st.nqwait == 1) ? 1 : 0; // save ACOR for the order-up estimate
-            if (st.flag) st.conp = st.tq[5];
-            st.flag2 = (fabs(st.etamax - 1.0) > 0.0) ? 1 : 0;
-            T0_END
-            if (st.flag && tid < NEQ) s.yh[st.lmax - 1][tid] = s.acor[tid];
-            if (st.flag2) {
-                // label 130: step/order selection
+            if (lvl == 2) {
+                // label 130 with NQWAIT = 0: order selection
                 double ddn = 0.0, dup = 0.0;
-                const bool full = (st.nqwait == 0); // block-uniform
-                if (full) {
-                    if (st.nq != 1) ddn = wrms_norm(s, b, s.yh[st.l - 1], s.ewt);
-                    if (st.l != st.lmax) {
-                        double cnquot = (st.tq[5] / st.conp) * pow(st.h / st.tau[2], (double)st.l);
-                        double t = 0.0;
-                        if (tid < NEQ) {
-                            double v = s.acor[tid] - cnquot * s.yh[st.lmax - 1][tid];
-                            s.savf[tid] = v;
-                            t = v * s.ewt[tid];
-                            t = t * t;
-                        }
-                        dup = sqrt(block_sum(s, b, t) / (double)NEQ);
+                if (st.nq != 1) ddn = wrms_norm(s, b, s.yh[st.l - 1], s.ewt);
+                if (st.l != st.lmax) {
+                    double cnquot = (st.tq[5] / st.conp) * pow(st.h / st.tau[2], (double)st.l);
+                    double t = 0.0;
+                    if (tid < NEQ) {
+                        double v = s.acor[tid] - cnquot * s.yh[st.lmax - 1][tid];
+                        s.savf[tid] = v;
+                        t = v * s.ewt[tid];
+                        t = t * t;
                     }
+                    dup = sqrt(block_sum(s, b, t) / (double)NEQ);
                 }
                 T0_BEGIN
                 double flotl = (double)st.l;
                 double etaq = 1.0 / (pow(V_BIAS2 * st.dsm, 1.0 / flotl) + V_ADDON);
                 int choose = 0;
                 st.flag = 0;
-                if (full) {
-                    st.nqwait = 2;
-                    double etaqm1 = 0.0, etaqp1 = 0.0;
-                    if (st.nq != 1) etaqm1 = 1.0 / (pow(V_BIAS1 * (ddn / st.tq[1]), 1.0 / (flotl - 1.0)) + V_ADDON);
-                    if (st.l != st.lmax) etaqp1 = 1.0 / (pow(V_BIAS3 * (dup / st.tq[3]), 1.0 / (flotl + 1.0)) + V_ADDON);
-                    if (etaq >= etaqp1) choose = (etaq < etaqm1) ? -1 : 0;
-                    else choose = (etaqp1 > etaqm1) ? 1 : -1;
-                    if (choose == -1) { st.eta = etaqm1; st.newq = st.nq - 1; }
-                    if (choose == 1) { st.eta = etaqp1; st.newq = st.nq + 1; st.flag = 1; }
-                }
+                st.nqwait = 2;
+                double etaqm1 = 0.0, etaqp1 = 0.0;
+                if (st.nq != 1) etaqm1 = 1.0 / (pow(V_BIAS1 * (ddn / st.tq[1]), 1.0 / (flotl - 1.0)) + V_ADDON);
+                if (st.l != st.lmax) etaqp1 = 1.0 / (pow(V_BIAS3 * (dup / st.tq[3]), 1.0 / (flotl + 1.0)) + V_ADDON);
+                if (etaq >= etaqp1) choose = (etaq < etaqm1) ? -1 : 0;
+                else choose = (etaqp1 > etaqm1) ? 1 : -1;
+                if (choose == -1) { st.eta = etaqm1; st.newq = st.nq - 1; }
+                if (choose == 1) { st.eta = etaqp1; st.newq = st.nq + 1; st.flag = 1; }
                 if (choose == 0) { st.eta = etaq; st.newq = st.nq; }
                 if (st.eta < V_THRESH || fabs(st.etamax - 1.0) <= 0.0) {
                     st.newq = st.nq;
@@ -493,23 +560,16 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
                     st.newh = 1;
                     st.hnew = st.h * st.eta;
                 }
+                // label 250
+                st.etamax = V_ETAMX3;
+                if (st.nst_call <= 10) st.etamax = V_ETAMX2;
+                st.jstart = 1;
                 T0_END
                 if (st.flag && tid < NEQ) s.yh[st.lmax - 1][tid] = s.acor[tid];
-            } else {
-                T0_BEGIN
-                if (st.nqwait < 2) st.nqwait = 2;
-                st.newq = st.nq;
-                st.newh = 0;
-                st.eta = 1.0;
-                st.hnew = st.h;
-                T0_END
             }
             // label 250
             if (tid < NEQ) s.acor[tid] *= 1.0 / st.tq[2];
-            T0_BEGIN
-            st.etamax = V_ETAMX3;
-            if (st.nst_call <= 10) st.etamax = V_ETAMX2;
-            T0_END
+            booked = true;
             break;
         }
         // ---- label 100: error test failed ----
@@ -541,18 +601,24 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
             st.nqwait = 10;
             st.flag = 3;
         }
+        if (st.flag == 0) { // plain retry: label 60/70 in the same section
+            step_head_scalar(st, 1);
+            st.fz_head = 1;
+        } else st.fz_head = 0;
         T0_END
         int f = st.flag;
         if (f == 1) break;
-        if (f == 0) { do_rescale = 1; continue; }
+        if (f == 0) { do_rescale = 1; head_done = st.fz_head; continue; }
         if (f == 2) {
             vjust_dev(s, -1);
             T0_BEGIN
             st.l = st.nq;
             st.nq = st.nq - 1;
             st.nqwait = st.l;
+            step_head_scalar(st, 1);
             T0_END
             do_rescale = 1;
+            head_done = 1;
             continue;
         }
         // f == 3 (label 120): reload YH(:,2) = H*F(TN, Y) at the last corrector iterate
@@ -560,9 +626,11 @@ __device__ __noinline__ void vstep_dev(Smem &s, Blk &b)
         if (tid < NEQ) s.yh[1][tid] = st.h * s.savf[tid];
         do_rescale = 0;
     }
-    T0_BEGIN
-    st.jstart = 1;
-    T0_END
+    if (!booked) {
+        T0_BEGIN
+        st.jstart = 1;
+        T0_END
+    }
 }
 
 // One DVODE call (ISTATE=1, ITASK=1): integrate s.abund from st.current_time to tout.

@@ -34,11 +34,9 @@
 #define LMAXORD 6
 #define NEQP ((NEQ + 7) & ~7)
 #define NAUGP ((NAUG + 7) & ~7)
-#define GJ_R 4
-#define GJ_C 5
-#define GJ_TR ((MDENSE + GJ_R - 1) / GJ_R)
-#define GJ_TC ((MDENSE + GJ_C - 1) / GJ_C)
-#define GJ_PAD (((MDENSE > GJ_TR * GJ_R ? MDENSE : GJ_TR * GJ_R) > GJ_TC * GJ_C ? (MDENSE > GJ_TR * GJ_R ? MDENSE : GJ_TR * GJ_R) : GJ_TC * GJ_C) + 4)
+#define GJ_B 5                              /* square register tile of the dense Gauss-Jordan inverse */
+#define GJ_NT ((MDENSE + GJ_B - 1) / GJ_B)  /* tiles per side */
+#define GJ_PAD (GJ_NT * GJ_B + 4)
 
 // ---- constants.f90:2-18, surfacereactions.f90:34-52 (single-precision literals kept)
 #define C_KBOLTZ 1.38065040e-16
@@ -68,6 +66,7 @@ struct Scalars {
     long long step_budget;
     // RHS ext quantities at the last evaluated state
     double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S;
+    double dflux[2]; // fluxes of the deferred photo reactions (H2 + hv, CO + hv)
     // hotcore / cshock
     double max_temp, vs, timestep_factor, min_postshock_temp;
     double cs_dlength, cs_z1, cs_z2, cs_z3, cs_v0, cs_at, cs_vn0, cs_zn0, cs_dissipation_time, cs_max_temp,
@@ -84,6 +83,7 @@ struct Scalars {
     long long nsing, nmaxcor, ndiverge, nfailcall;
     long long cyc_rates, cyc_rhs, cyc_jac, cyc_factor, cyc_dense, cyc_solve, cyc_total;
     int flag, flag2; // block-wide decisions published by thread 0
+    int fz_level, fz_save, fz_head; // how far the fused scalar sections got (engine_bdf.cuh)
     double dbg[64];
 };
 

@@ -11,22 +11,21 @@
 // desc[slot] = {term_begin, target | nterms<<16 | log2(team)<<28}; teams are aligned
 // power-of-two groups of consecutive slots; lane l of a team sums terms l, l+T, ...
 // A program is a list of units (one pass of NT slots of one level; units[k] = {first slot,
-// end slot | barrier-after << 31}, in constant memory); levels are separated by block
-// barriers.  A warp whose 32 slots lie beyond the unit's end goes straight to the barrier:
+// end slot | sync-after << 30}, in constant memory); levels are separated by block barriers, or by
+// a warp-level sync where consecutive levels fit in the 32 slots of warp 0.  A warp whose 32 slots lie beyond the unit's end goes straight to the barrier:
 // most solve levels only occupy a few warps, and issue slots -- not bandwidth -- are what
 // these phases cost.
 //
 // The tables live in L2 (the shared-memory carve-out leaves only ~28 KB of L1), and a level is
 // a dependent chain descriptor -> terms -> shared-memory operands.  None of the table reads
-// depends on numeric data, so the executor runs ahead of the level barriers: the descriptor (and
-// the optional per-target `pre` word) of unit k+1 is loaded into registers while unit k computes,
-// and the term lines of unit k+1 are pulled into L1 with prefetch instructions before the barrier
-// of unit k.  Device functions only get ~60 registers here (the call chain shares the 128 of a
-// 512-thread CTA), so the terms themselves are not held in registers across the barrier.
+// depends on numeric data, so the executor is software-pipelined across the level barriers:
+// while unit k computes, the first U terms per lane (and the optional per-target `pre` word) of
+// unit k+1 and the descriptor of unit k+2 are already in flight.  Only rows longer than U terms
+// per lane fetch a second batch inside their own level.  (prefetch.global.L1 instead of register
+// staging was measured first: the L1 hit rate barely moved and the term loads stayed exposed.)
 struct TeamSlot {
     uint2 d;       // descriptor
     uint32_t sl;   // slot index
-    uint32_t aux;  // pre(target)
     bool warp_on;  // this warp has slots in the unit (warp-uniform)
 };
 
@@ -37,8 +36,6 @@ __device__ __forceinline__ double masked_fma(double a, double x, double acc, boo
     return acc;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
 template <int U, class TermT, class TermF, class PreF, class FinF>
 __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, const TermT *__restrict__ terms,
                                            const uint32_t *units, int nunits, TermF term, PreF pre, FinF fin)
@@ -46,56 +43,67 @@ __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, co
     const uint2 *d2 = reinterpret_cast<const uint2 *>(desc);
     const uint2 *units2 = reinterpret_cast<const uint2 *>(units);
     const uint32_t lane = threadIdx.x & 31u;
-    constexpr uint32_t PER_LINE = 128u / sizeof(TermT);
     auto fetch_desc = [&](int k) {
         TeamSlot t;
         t.d = make_uint2(0u, 0xFFFFu);
         t.sl = 0u;
-        t.aux = 0u;
         t.warp_on = false;
         if (k < nunits) {
             const uint2 un = units2[k];
             t.sl = un.x + threadIdx.x;
-            t.warp_on = t.sl - lane < (un.y & 0x7FFFFFFFu); // slot ranges are padded to multiples of 32
+            t.warp_on = t.sl - lane < (un.y & 0x3FFFFFFFu); // slot ranges are padded to multiples of 32
             if (t.warp_on) t.d = __ldg(d2 + t.sl);
         }
         return t;
     };
-    // second half of the look-ahead (needs the descriptor to have arrived): term lines -> L1, pre word
-    auto look_ahead = [&](TeamSlot &t) {
-        const uint32_t target = t.d.y & 0xFFFFu, n = (t.d.y >> 16) & 0xFFFu;
+    // first term batch of a unit: unconditional loads (the generator pads every term table by 32*U
+    // entries, and whatever follows a row are valid terms of other rows); masked when summed
+    auto fetch_terms = [&](const TeamSlot &t, TermT (&tb)[U], uint32_t &aux) {
+        const uint32_t target = t.d.y & 0xFFFFu;
         const uint32_t T = 1u << ((t.d.y >> 28) & 7u), lit = t.sl & (T - 1u);
+        aux = 0u;
         if (target != 0xFFFFu) {
-            const TermT *tp = terms + t.d.x;
-            if (lit * PER_LINE < n) prefetch_l1(tp + lit * PER_LINE);
-            if (lit == 0u) {
-                prefetch_l1(tp + n - 1u);
-                t.aux = pre(target);
-            }
+            const TermT *tp = terms + t.d.x + lit;
+#pragma unroll
+            for (int u = 0; u < U; u++) tb[u] = __ldg(tp + (uint32_t)u * T);
+            if (lit == 0u) aux = pre(target);
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) tb[u] = TermT{};
         }
     };
-    TeamSlot cur = fetch_desc(0);
-    look_ahead(cur);
+    TeamSlot cur = fetch_desc(0), nxt = fetch_desc(1);
+    TermT tb[U];
+    uint32_t aux;
+    fetch_terms(cur, tb, aux);
     for (int k = 0; k < nunits; k++) {
-        TeamSlot nxt = fetch_desc(k + 1); // in flight while unit k computes
+        // ---- look-ahead: descriptor of unit k+2, first term batch of unit k+1 ----
+        const TeamSlot nn = fetch_desc(k + 2);
+        TermT tbn[U];
+        uint32_t auxn;
+        fetch_terms(nxt, tbn, auxn);
+        // ---- unit k ----
         if (cur.warp_on) {
             const uint32_t target = cur.d.y & 0xFFFFu, n = (cur.d.y >> 16) & 0xFFFu;
             const int tl = (int)((cur.d.y >> 28) & 7u);
             const uint32_t T = 1u << tl, lit = cur.sl & (T - 1u);
             double acc = 0.0;
             if (target != 0xFFFFu) {
-                // branch-free batch: U unconditional table loads (the generator pads every term table
-                // by 32*U entries, and whatever follows a row are valid terms of other rows), then all
-                // shared-memory operand loads, then one chain of masked FMAs in term order
-                const TermT *tp = terms + cur.d.x + lit;
-                for (uint32_t q0 = lit; q0 < n; q0 += T * U, tp += T * U) {
-                    TermT tb[U];
+                // branch-free batch: all shared-memory operand loads, then one chain of masked FMAs
+                double2 ax[U];
 #pragma unroll
-                    for (int u = 0; u < U; u++) tb[u] = __ldg(tp + (uint32_t)u * T);
-                    double2 ax[U];
+                for (int u = 0; u < U; u++) ax[u] = term(tb[u]);
+                asm volatile("" ::: "memory"); // issue every operand load before the dependent FMA chain
 #pragma unroll
-                    for (int u = 0; u < U; u++) ax[u] = term(tb[u]);
-                    asm volatile("" ::: "memory"); // issue every operand load before the dependent FMA chain
+                for (int u = 0; u < U; u++) acc = masked_fma(ax[u].x, ax[u].y, acc, lit + (uint32_t)u * T < n);
+                const TermT *tp = terms + cur.d.x + lit + T * U;
+                for (uint32_t q0 = lit + T * U; q0 < n; q0 += T * U, tp += T * U) {
+                    TermT tc[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) tc[u] = __ldg(tp + (uint32_t)u * T);
+#pragma unroll
+                    for (int u = 0; u < U; u++) ax[u] = term(tc[u]);
+                    asm volatile("" ::: "memory");
 #pragma unroll
                     for (int u = 0; u < U; u++) acc = masked_fma(ax[u].x, ax[u].y, acc, q0 + (uint32_t)u * T < n);
                 }
@@ -105,13 +113,22 @@ __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, co
                 double v = __shfl_xor_sync(0xffffffffu, acc, o);
                 if ((uint32_t)o < T) acc += v;
             }
-            if (target != 0xFFFFu && lit == 0u) fin(target, acc, cur.aux);
+            if (target != 0xFFFFu && lit == 0u) fin(target, acc, aux);
         }
-        look_ahead(nxt);
-        if (units2[k].y >> 31) BLOCK_SYNC();
+        const uint32_t sync = units2[k].y >> 30; // 2: block barrier, 1: the next level also lives in warp 0
+        if (sync & 2u) BLOCK_SYNC();
+        else if (sync) __syncwarp();
         cur = nxt;
+        nxt = nn;
+        aux = auxn;
+#pragma unroll
+        for (int u = 0; u < U; u++) tb[u] = tbn[u];
     }
 }
+
+// the 14 worker warps of rhs_eval (the last two warps evaluate the deferred photo rates)
+#define NWORK (NT - 64)
+#define WORK_SYNC() asm volatile("barrier.sync 3, %0;" ::"n"(NWORK) : "memory")
 
 // flux_r = rate_r * prod_k yext[f_rk]  (reaction.py:779-819); one packed 8-byte entry per reaction
 __device__ __forceinline__ void flux_range(Smem &s, int begin, int end, int first, int stride)
@@ -141,53 +158,76 @@ __device__ __noinline__ void rhs_eval(Smem &s, double *ydot)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const double *y = s.y;
     TIMER_START
-    // ---- phase A: ext scalars + H2 photo rate (warp 0) | CO photo rate (warp 1) | plain fluxes ----
-    if (warp == 0) {
-        double sm = fmax(1e-30, y[NET_IS]), sb = fmax(1e-30, y[NET_IB]);
-        double blr = fmin(1.0, NET_NSITES / (NET_GDR * sb));
-        double ism = 1.0 / sm;
-        double ts = 0.0;
-        for (int k = lane; k < NET_NSWAP; k += 32) {
-            int r = NET_SWAP_LO + k;
-            ts += s.rate[r] * y[net_re1[r]] * blr;
-        }
-        ts = warp_sum(ts);
+    if (warp >= NWARPS - 2) {
+        // ---- photo warps: the two rates that follow the state (chemistry.f90:311-319) are long
+        // single-lane chains (log10/pow/exp, spline walks).  They run here, next to the flux and
+        // gather phases of the 14 worker warps; their reactions are not in the flux table / gather
+        // program and are added to ydot after the gather (net_deferred_*).
         if (lane == 0) {
-            // y[NEQ+0] (the constant-one padding factor) is set once per CTA at kernel start
-            s.y[NEQ + 1] = blr;
-            s.y[NEQ + 2] = ism;
-            s.y[NEQ + 3] = ts * ism;
-            st.e_sm = sm; st.e_sb = sb; st.e_blr = blr; st.e_ism = ism; st.e_tsw = ts * ism;
-            st.e_dblr = (blr >= 1.0 || y[NET_IB] <= 1e-30) ? 0.0 : -blr / sb;
-            st.e_dism = (y[NET_IS] <= 1e-30) ? 0.0 : -ism * ism;
-            // chemistry.f90:311-319: the H2 photo rate follows the current H2 abundance
-            double h2col = 0.0 + 0.5 * y[NET_NH2] * y[NET_ID] * (st.cloudsize / (double)1.0f);
-            s.rate[NET_NR_H2_HV] = st.scat_h2_pre * h2_self_shielding_dev(h2col);
+            const double d = y[NET_ID];
+            const double h2col = 0.0 + 0.5 * y[NET_NH2] * d * (st.cloudsize / (double)1.0f);
+            if (warp == NWARPS - 2) {
+                const double k = st.scat_h2_pre * h2_self_shielding_dev(h2col);
+                s.rate[NET_NR_H2_HV] = k;
+                const double f = k * y[NET_DEFERRED_RE_H2];
+                s.flux[NET_NR_H2_HV] = f;
+                st.dflux[0] = f;
+            } else {
+                const double cocol = 0.0 + 0.5 * y[NET_NCO] * d * (st.cloudsize / (double)1.0f);
+                st.cocol = cocol;
+                st.h2col = h2col;
+                const double k = co_photo_rate_dev(h2col, cocol, st.radfield, st.av);
+                s.rate[NET_NR_CO_HV] = k;
+                const double f = k * y[NET_DEFERRED_RE_CO];
+                s.flux[NET_NR_CO_HV] = f;
+                st.dflux[1] = f;
+            }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            double d = y[NET_ID];
-            double cocol = 0.0 + 0.5 * y[NET_NCO] * d * (st.cloudsize / (double)1.0f);
-            double h2col = 0.0 + 0.5 * y[NET_NH2] * d * (st.cloudsize / (double)1.0f);
-            st.cocol = cocol;
-            st.h2col = h2col;
-            s.rate[NET_NR_CO_HV] = co_photo_rate_dev(h2col, cocol, st.radfield, st.av);
-        }
+        BLOCK_SYNC(); // pairs with the barrier that ends the gather
     } else {
-        flux_range(s, 0, NET_NPLAIN, tid - 64, NT - 64);
-    }
-    BLOCK_SYNC();
-    // ---- phase B: fluxes that need ext factors or the fresh photo rates --------------------
-    flux_range(s, NET_NPLAIN, NREAC, tid, NT);
-    BLOCK_SYNC();
-    // ---- gather: ydot_i = sum of signed fluxes (io_functions.py:562-581) ---------------------
-    {
+        // ---- phase A: ext scalars (warp 0) | plain fluxes (warps 1..13) ----
+        if (warp == 0) {
+            double sm = fmax(1e-30, y[NET_IS]), sb = fmax(1e-30, y[NET_IB]);
+            double blr = fmin(1.0, NET_NSITES / (NET_GDR * sb));
+            double ism = 1.0 / sm;
+            double ts = 0.0;
+            for (int k = lane; k < NET_NSWAP; k += 32) {
+                int r = NET_SWAP_LO + k;
+                ts += s.rate[r] * y[net_re1[r]] * blr;
+            }
+            ts = warp_sum(ts);
+            if (lane == 0) {
+                // y[NEQ+0] (the constant-one padding factor) is set once per CTA at kernel start
+                s.y[NEQ + 1] = blr;
+                s.y[NEQ + 2] = ism;
+                s.y[NEQ + 3] = ts * ism;
+                st.e_sm = sm; st.e_sb = sb; st.e_blr = blr; st.e_ism = ism; st.e_tsw = ts * ism;
+                st.e_dblr = (blr >= 1.0 || y[NET_IB] <= 1e-30) ? 0.0 : -blr / sb;
+                st.e_dism = (y[NET_IS] <= 1e-30) ? 0.0 : -ism * ism;
+            }
+        } else {
+            flux_range(s, 0, NET_NPLAIN, tid - 32, NWORK - 32);
+        }
+        WORK_SYNC();
+        // ---- phase B: fluxes that need the ext factors ----------------------------------------
+        flux_range(s, NET_NPLAIN, NET_NFLUX, tid, NWORK);
+        WORK_SYNC();
+        // ---- gather: ydot_i = sum of signed fluxes (io_functions.py:562-581); units of NWORK slots;
+        // ends with the block barrier the photo warps arrive at when their rates are done ----------
         const double *flux = s.flux;
         run_levels<8>(
             net_gather_desc, net_gather_terms, net_gather_units, NET_GATHER_NUNITS,
             [&](uint16_t t) { return make_double2(flux[t & 0x7FFFu], (t & 0x8000u) ? -1.0 : 1.0); },
             [](uint32_t) { return 0u; },
             [&](uint32_t target, double acc, uint32_t) { ydot[target] = acc; });
+    }
+    if (tid == NSURF + 1) {
+        // deferred photo reactions (gas-phase rows only: disjoint from the surface/bulk sums below)
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int i = net_deferred_spec[k];
+            if (i >= 0) ydot[i] += (double)net_deferred_sign[k] * st.dflux[k >> 2];
+        }
     }
     // ---- three-phase transfer odes.f90:4815-5180 ------------------------------------------------
     {
@@ -348,86 +388,102 @@ __device__ __forceinline__ void constraint_rhs(Smem &s)
     BLOCK_SYNC();
 }
 
+// Newton right-hand side in elimination order, constraint rows included, in one pass:
+// xs[new] = rl1*h*savf[o] - (rl1*yh1[o] + acor[o]) (DVNLSD, dvode.f90:7995-8000) for the plain rows;
+// the BULK / SURFACE rows get r - sum(member r) (see constraint_rhs) from warps 0/1, which recompute
+// the member residuals instead of reading them back (one barrier less per corrector iteration).
+// Ends with a barrier.
+__device__ __forceinline__ void newton_rhs(Smem &s)
+{
+    const Scalars &st = s.st;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double c1 = st.rl1 * st.h, rl1 = st.rl1;
+    auto resid = [&](int o) { return c1 * s.savf[o] - (rl1 * s.yh[1][o] + s.acor[o]); };
+    if (warp < 2) {
+        const int16_t *list = warp == 0 ? net_surface_list : net_bulk_list;
+        double acc = 0.0;
+        for (int k = lane; k < NSURF; k += 32) acc += resid(list[k]);
+        acc = warp_sum(acc);
+        const int o = warp == 0 ? NET_IS : NET_IB;
+        if (lane == 0) s.xs[net_iperm[o]] = resid(o) - acc;
+    }
+    if (tid < NAUG) {
+        int o = net_perm[tid];
+        if (o != NET_IS && o != NET_IB) s.xs[tid] = (o < NEQ) ? resid(o) : 0.0;
+    }
+    BLOCK_SYNC();
+}
+
 // In-place inverse of the dense trailing block by Gauss-Jordan elimination without
-// pivoting.  Each thread keeps a GJ_R x GJ_C tile of the block in registers for all M
-// steps; per step only the pivot row, pivot column and 1/pivot go through shared memory.
-// Every tile does the uniform update a_ij -= col_i * (row_j * p); only the few tiles that
-// contain the pivot row or column patch their entries afterwards (a_kj p, -a_ik p, p).
+// pivoting.  Each thread keeps a GJ_B x GJ_B tile of the block in registers for all M steps;
+// per step only the pivot row, pivot column and 1/pivot go through shared memory (double
+// buffered, one named barrier per step).  The step loop runs over diagonal tiles with the
+// GJ_B steps inside a tile unrolled, so "do I own the pivot row / column" is a comparison of
+// tile coordinates and every register index is static.  Every tile does the uniform update
+// a_ij -= col_i * (row_j * p); the tiles on the pivot's tile row / column then overwrite their
+// pivot row (a_kj p) / column (-a_ik p, p on the diagonal).
 __device__ __noinline__ bool dense_inverse(Smem &s)
 {
-    static_assert(GJ_TR * GJ_TC <= NT, "dense tile grid must fit the block");
+    static_assert(GJ_NT * GJ_NT <= NT, "dense tile grid must fit the block");
     const int tid = threadIdx.x;
     double *T = s.val + NET_OFF_DENSE;
-    const int tr = tid / GJ_TC, tc = tid - tr * GJ_TC;
-    const bool active = tid < GJ_TR * GJ_TC;
-    const int i0 = tr * GJ_R, j0 = tc * GJ_C;
-    double a[GJ_R][GJ_C];
+    const int tr = tid / GJ_NT, tc = tid - tr * GJ_NT;
+    const bool active = tid < GJ_NT * GJ_NT;
+    const int i0 = tr * GJ_B, j0 = tc * GJ_B;
+    double a[GJ_B][GJ_B];
 #pragma unroll
-    for (int r = 0; r < GJ_R; r++)
+    for (int r = 0; r < GJ_B; r++)
 #pragma unroll
-        for (int c = 0; c < GJ_C; c++) {
+        for (int c = 0; c < GJ_B; c++) {
             int i = i0 + r, j = j0 + c;
             a[r][c] = (active && i < MDENSE && j < MDENSE) ? T[i * MDENSE + j] : 0.0;
         }
     bool ok = true;
-    constexpr int GJ_NTHR = (GJ_TR * GJ_TC + 31) & ~31; // whole warps take part in the named barrier
+    constexpr int GJ_NTHR = (GJ_NT * GJ_NT + 31) & ~31; // whole warps take part in the named barrier
     if (tid < GJ_NTHR) {
-        for (int k = 0; k < MDENSE; k++) {
-            const int buf = k & 1;
-            const int rk = k - i0, ck = k - j0;
-            const bool own_r = active && (unsigned)rk < (unsigned)GJ_R, own_c = active && (unsigned)ck < (unsigned)GJ_C;
-            if (own_r) {
+        for (int kb = 0; kb < GJ_NT; kb++) {
+            const bool own_r = active && tr == kb, own_c = active && tc == kb;
 #pragma unroll
-                for (int r = 0; r < GJ_R; r++)
-                    if (r == rk) {
+            for (int kk = 0; kk < GJ_B; kk++) {
+                const int k = kb * GJ_B + kk;
+                if (k >= MDENSE) break; // block-uniform
+                const int buf = k & 1;
+                if (own_r) {
 #pragma unroll
-                        for (int c = 0; c < GJ_C; c++) s.gj_row[buf][j0 + c] = a[r][c];
-                    }
-            }
-            if (own_c) {
+                    for (int c = 0; c < GJ_B; c++) s.gj_row[buf][j0 + c] = a[kk][c];
+                }
+                if (own_c) {
 #pragma unroll
-                for (int c = 0; c < GJ_C; c++)
-                    if (c == ck) {
+                    for (int r = 0; r < GJ_B; r++) s.gj_col[buf][i0 + r] = a[r][kk];
+                    if (own_r) s.gj_piv[buf] = 1.0 / a[kk][kk];
+                }
+                asm volatile("barrier.sync 1, %0;" ::"r"(GJ_NTHR) : "memory");
+                const double p = s.gj_piv[buf];
+                if (!isfinite(p) || p == 0.0) ok = false;
+                double rp[GJ_B], cl[GJ_B];
 #pragma unroll
-                        for (int r = 0; r < GJ_R; r++) {
-                            s.gj_col[buf][i0 + r] = a[r][c];
-                            if (r == rk) s.gj_piv[buf] = 1.0 / a[r][c];
-                        }
-                    }
-            }
-            asm volatile("barrier.sync 1, %0;" ::"r"(GJ_NTHR) : "memory");
-            const double p = s.gj_piv[buf];
-            if (!isfinite(p) || p == 0.0) ok = false;
-            double rp[GJ_C], cl[GJ_R];
+                for (int c = 0; c < GJ_B; c++) rp[c] = s.gj_row[buf][j0 + c] * p;
 #pragma unroll
-            for (int c = 0; c < GJ_C; c++) rp[c] = s.gj_row[buf][j0 + c] * p;
+                for (int r = 0; r < GJ_B; r++) cl[r] = s.gj_col[buf][i0 + r];
 #pragma unroll
-            for (int r = 0; r < GJ_R; r++) cl[r] = s.gj_col[buf][i0 + r];
+                for (int r = 0; r < GJ_B; r++)
 #pragma unroll
-            for (int r = 0; r < GJ_R; r++)
+                    for (int c = 0; c < GJ_B; c++) a[r][c] -= cl[r] * rp[c];
+                if (own_r) {
 #pragma unroll
-                for (int c = 0; c < GJ_C; c++) a[r][c] -= cl[r] * rp[c];
-            if (own_r) {
+                    for (int c = 0; c < GJ_B; c++) a[kk][c] = rp[c];
+                }
+                if (own_c) {
 #pragma unroll
-                for (int r = 0; r < GJ_R; r++)
-                    if (r == rk) {
-#pragma unroll
-                        for (int c = 0; c < GJ_C; c++) a[r][c] = rp[c];
-                    }
-            }
-            if (own_c) {
-#pragma unroll
-                for (int c = 0; c < GJ_C; c++)
-                    if (c == ck) {
-#pragma unroll
-                        for (int r = 0; r < GJ_R; r++) a[r][c] = (r == rk) ? p : -cl[r] * p;
-                    }
+                    for (int r = 0; r < GJ_B; r++) a[r][kk] = -cl[r] * p;
+                    if (own_r) a[kk][kk] = p;
+                }
             }
         }
 #pragma unroll
-        for (int r = 0; r < GJ_R; r++)
+        for (int r = 0; r < GJ_B; r++)
 #pragma unroll
-            for (int c = 0; c < GJ_C; c++) {
+            for (int c = 0; c < GJ_B; c++) {
                 int i = i0 + r, j = j0 + c;
                 if (active && i < MDENSE && j < MDENSE) T[i * MDENSE + j] = a[r][c];
             }
@@ -475,7 +531,7 @@ __device__ __noinline__ void lin_solve(Smem &s)
     double *xs = s.xs;
     TIMER_START
     // forward substitution through the sparse rows, then b_T -= L21 x (one program: fwd levels + tail)
-    run_levels<8>(
+    run_levels<4>(
         net_fwd_desc, net_fwd_terms, net_fwd_units, NET_FWD_NUNITS,
         [&](uint32_t t) { return make_double2(val[t >> 16], xs[t & 0xFFFFu]); },
         [](uint32_t) { return 0u; },
@@ -496,7 +552,7 @@ __device__ __noinline__ void lin_solve(Smem &s)
     BLOCK_SYNC();
     if (tid < MDENSE) xs[NET_N0 + tid] = s.tmpv[tid];
     BLOCK_SYNC();
-    run_levels<8>(
+    run_levels<4>(
         net_bwd_desc, net_bwd_terms, net_bwd_units, NET_BWD_NUNITS,
         [&](uint32_t t) { return make_double2(val[t >> 16], xs[t & 0xFFFFu]); },
         [](uint32_t) { return 0u; },

@@ -36,6 +36,7 @@ from .network import N_EXT, TYPE_ID, TYPE_NAMES, Network
 
 NTHREADS = 512
 NULL_TARGET = 0xFFFF
+SOLVE_TERMS_PER_LANE = 4  # solve levels are latency chains: short per-lane chains, wider teams
 TERM_PAD = 256  # >= 32 lanes x 8 terms per batch
 
 
@@ -108,6 +109,12 @@ class Generated:
         neq = sym.neq
         # ydot gather: term = reaction | neg<<15
         assert net.nreac < (1 << 15), "gather term packing needs nreac < 32768"
+        # Deferred reactions: the two photo rates that follow the state (H2 self-shielding, CO
+        # shielding) are long single-lane chains.  Two warps of the CTA evaluate them while the other
+        # warps do the fluxes and the gather, so their fluxes are not part of the flux table / gather
+        # program: the RHS adds them to ydot afterwards (deferred_spec / deferred_sign per reaction).
+        self.deferred = [int(net.reaction_idx["nR_H2_hv"]), int(net.reaction_idx["nR_CO_hv"])]
+        self.deferred_rows = {r: [] for r in self.deferred}
         items = []
         for i in range(net.nspec):
             a, b = sym.g_ptr[i], sym.g_ptr[i + 1]
@@ -115,20 +122,27 @@ class Generated:
                 continue  # BULK / SURFACE totals are written by the transfer phase of the RHS
             terms = []
             for r, sg in zip(sym.g_reac[a:b], sym.g_sign[a:b]):
+                if int(r) in self.deferred_rows:
+                    self.deferred_rows[int(r)].append((i, int(sg)))
+                    continue
                 t = int(r) | ((1 << 15) if sg < 0 else 0)
                 terms.append(t)
             items.append((i, terms))
+        for r in self.deferred:
+            # one plain reactant, no ext factors: flux = rate * y[reactant]
+            assert (sym.flux_f[r][1:] >= neq).all() and sym.flux_f[r][0] < net.nspec, "deferred reactions are unimolecular"
+            assert all(i < net.nspec and i not in net.surface_list and i not in net.bulk_list for i, _ in self.deferred_rows[r])
         self.gather = TeamProgram(items)
         self.flux_f = sym.flux_f.astype(np.int16)
         # reactions whose flux needs an ext factor (blr, 1/safeMantle, tau) or a per-RHS photo rate
         ext = (sym.flux_f > neq).any(axis=1)
-        ext[net.reaction_idx["nR_H2_hv"]] = True
-        ext[net.reaction_idx["nR_CO_hv"]] = True
-        self.flux_order = np.concatenate([np.where(~ext)[0], np.where(ext)[0]]).astype(np.int32)
-        self.n_plain = int((~ext).sum())
+        keep = np.ones(net.nreac, bool)
+        keep[self.deferred] = False
+        self.flux_order = np.concatenate([np.where(~ext & keep)[0], np.where(ext & keep)[0]]).astype(np.int32)
+        self.n_plain = int((~ext & keep).sum())
         ff = np.full((net.nreac, 4), neq + 0, np.int64)
         ff[:, : sym.fwidth] = sym.flux_f
-        tab = np.zeros((net.nreac, 2), np.uint32)
+        tab = np.zeros((len(self.flux_order), 2), np.uint32)
         for idx, r in enumerate(self.flux_order):
             f = ff[r]
             tab[idx, 0] = int(r) | (int(f[0]) << 16)
@@ -167,7 +181,7 @@ class Generated:
                 for e, n in enumerate(L["rows"]):
                     a, b = L["ptr"][e], L["ptr"][e + 1]
                     items.append((int(n), [(int(p) << 16) | int(c) for p, c in zip(L["pos"][a:b], L["cols"][a:b])]))
-                out.append(TeamProgram(items, terms_per_lane=8))
+                out.append(TeamProgram(items, terms_per_lane=SOLVE_TERMS_PER_LANE))
             return out
         self.fwd = lvl(sym.fwd_levels)
         self.bwd = lvl(sym.bwd_levels)
@@ -446,9 +460,20 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     w(_c_array("net_sco_rows", ph["sco_rows"], "double", qual="__constant__"))
     w(_c_array("net_sco_d2", ph["sco_d2"], "double", qual="__constant__"))
     w("\n// ---- RHS: flux table + gather program ---------------------------------------------\n")
-    w(f"#define NET_NPLAIN {gen.n_plain}\n")
+    w(f"#define NET_NPLAIN {gen.n_plain}\n#define NET_NFLUX {len(gen.flux_order)}\n")
     w(_c_array("net_flux_tab", gen.flux_tab, "uint32_t"))
-    _emit_program(w, "net_gather", [gen.gather], term16=True)
+    # deferred photo reactions: {species, sign} rows, 4 slots per reaction (H2 + hv, CO + hv), -1 padded
+    dspec, dsign = [], []
+    for r in gen.deferred:
+        rows = gen.deferred_rows[r]
+        assert len(rows) <= 4
+        dspec += [i for i, _ in rows] + [-1] * (4 - len(rows))
+        dsign += [sg for _, sg in rows] + [0] * (4 - len(rows))
+    w(_c_array("net_deferred_spec", dspec, "int16_t"))
+    w(_c_array("net_deferred_sign", dsign, "int8_t"))
+    w(f"#define NET_DEFERRED_RE_H2 {int(sym.flux_f[gen.deferred[0]][0])}\n#define NET_DEFERRED_RE_CO {int(sym.flux_f[gen.deferred[1]][0])}\n")
+    # the last two warps of the CTA evaluate the deferred photo rates during the gather
+    _emit_program(w, "net_gather", [gen.gather], term16=True, nthreads=NTHREADS - 64)
     w("\n// ---- analytic Jacobian assembly ---------------------------------------------------\n")
     _emit_program(w, "net_jac", [gen.jac], term64=True)
     w(_c_array("net_diag_pos", sym.diag_pos, "uint16_t"))
@@ -458,8 +483,8 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     w("\n// ---- symbolic LU: factor levels, dense block, solves ---------------------------------\n")
     _emit_program(w, "net_factor", [p for p, _ in gen.factor])
     w(_c_array("net_factor_diag", gen.factor_diag_table(), "uint16_t"))
-    _emit_program(w, "net_fwd", gen.fwd + [gen.tail])  # forward levels, then b_T -= L21 x
-    _emit_program(w, "net_bwd", gen.bwd)
+    _emit_program(w, "net_fwd", gen.fwd + [gen.tail], warp_chains=True)  # forward levels, then b_T -= L21 x
+    _emit_program(w, "net_bwd", gen.bwd, warp_chains=True)
     w(_c_array("net_perm", sym.perm, "uint16_t"))
     w(_c_array("net_iperm", sym.iperm, "uint16_t"))
     path = outdir / "net_tables.cuh"
@@ -469,7 +494,7 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     return path
 
 
-def _emit_program(w, name, programs, term16=False, term64=False):
+def _emit_program(w, name, programs, term16=False, term64=False, warp_chains=False, nthreads=NTHREADS):
     """Concatenate level programs: desc (uint2 per slot), terms, level slot ranges."""
     desc, terms, lv = [], [], [0]
     for p in programs:
@@ -498,12 +523,17 @@ def _emit_program(w, name, programs, term16=False, term64=False):
         w(_c_array(name + "_terms", terms, "uint32_t"))
     w(_c_array(name + "_levels", lv, "uint32_t"))
     # unit table: one entry per (level, pass of NTHREADS slots): {first slot, end slot | barrier-after flag << 31}
+    # sync after a unit: bit 31 = block barrier; bit 30 = warp-level sync only -- this level and the next
+    # both fit in the 32 slots of warp 0, so the chain of tiny levels at the tail of a triangular solve
+    # runs inside one warp while the other warps wait at the next block barrier
     units = []
     for k in range(len(programs)):
         b0, e0 = lv[k], lv[k + 1]
-        starts = list(range(b0, e0, NTHREADS)) or [b0]
+        starts = list(range(b0, e0, nthreads)) or [b0]
+        warp_local = (warp_chains and k + 1 < len(programs) and e0 - b0 <= 32 and lv[k + 2] - lv[k + 1] <= 32)
         for i, st in enumerate(starts):
-            units.append((st, e0 | ((1 << 31) if i == len(starts) - 1 else 0)))
+            last = i == len(starts) - 1
+            units.append((st, e0 | (((1 << 30) if warp_local else (1 << 31)) if last else 0)))
     w(f"#define {name.upper()}_NUNITS {len(units)}\n")
     # unit tables are read with a block-uniform index: constant memory (no L2 round trip per level)
     w(_c_array(name + "_units", np.asarray(units, dtype=np.uint64).ravel(), "uint32_t", qual="__constant__"))
