@@ -126,17 +126,66 @@ def bounded_cells(ncell):
     return np.where(ok)[0]
 
 
-def run_oracle_sample(params, cores, offset=0):
-    """Time the CPU restatement on `cores` evenly spaced (bounded) cells of the workload, one per core."""
+def sample_cells(ncell, n, offset=0):
+    """`n` evenly spaced cells of the workload (deterministic; `offset` shifts the comb)."""
+    return (np.linspace(0, ncell - 1, n).astype(int) + offset) % ncell
+
+
+def run_oracle_sample(params, cores, offset=0, deadline_s=90.0):
+    """Time the CPU restatement on `cores` evenly spaced cells of the workload, one per core, with a
+    wall-clock bound: a model still running after `deadline_s` is stopped (oracle guard, flag -98) and
+    does not count.  Returns (models/s over the cells that finished, seconds, cell indices, y, flag)."""
     from oracle.oracle import Oracle
     from uclchem_b200.network import load_default
-    ncell = params.shape[1]
-    idx = (np.linspace(0, ncell - 1, cores).astype(int) + offset) % ncell
+    idx = sample_cells(params.shape[1], cores, offset)
     orc = Oracle(load_default())
+    orc.set_deadline(deadline_s)
     t0 = time.perf_counter()
     y, _, flag, _ = orc.run_grid(0, np.ascontiguousarray(params[:, idx]), nthreads=cores)
     dt = time.perf_counter() - t0
-    return len(idx) / dt, dt, idx, y, flag
+    orc.set_deadline(0.0)
+    done = int((flag != Oracle.FLAG_DEADLINE).sum())
+    return done / dt, dt, idx, y, flag
+
+
+def sample_text(idx, flag, dt, deadline_s):
+    cut = int((flag == -98).sum())
+    txt = f"{len(idx)} evenly spaced cells of the workload, one per host core, {dt:.1f} s"
+    if cut:
+        txt += (f"; {cut} of them were still running at the {deadline_s:.0f} s bound and are not counted "
+                "(the figure is then an upper bound of the CPU rate)")
+    return txt
+
+
+def assemble_line(*, a, world, ncell, workload, dt, kernel_ms, dt_e2e, launches, launches_e2e, stats, flags,
+                  clocks, work_model, fp64_peak_tflops, h2d_bytes, d2h_bytes, cpu, parity, traffic, stat_fields):
+    """The bench JSON line from measured quantities (pure function: unit-tested on the CPU)."""
+    f_rhs, f_jac, f_lu, f_solve, f_rates, b_interval = list(work_model)[:6]
+    S = {k: stats[:, i].astype(np.float64).sum() for i, k in enumerate(stat_fields)}
+    w_flop = (S["nfe"] * f_rhs + S["nje"] * f_jac + S["nlu"] * f_lu + S["nni"] * f_solve + S["nintervals"] * f_rates)
+    w_bytes = S["nintervals"] * b_interval
+    kern_s = kernel_ms / 1e3 / a.steps          # one launch per step
+    peak, how = peak_hbm()
+    roof = {"bound": "hbm", "achieved": w_bytes / kern_s / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": w_bytes / kern_s / 1e9 / peak, "traffic": traffic, "peak_source": how,
+            "note": "state is chip-resident per cell: HBM traffic is only cell load/store, the kernel is bound "
+                    "by dependent-instruction latency (shared memory, barriers) and the fp64 pipe, see fp64"}
+    fp64 = {"achieved_tflops": w_flop / kern_s / 1e12, "peak_tflops": fp64_peak_tflops,
+            "frac": w_flop / kern_s / 1e12 / fp64_peak_tflops if fp64_peak_tflops else None,
+            "peak_source": "DFMA micro-benchmark run by this process (uclgpu_fp64_peak)"}
+    return {
+        "metric": METRIC, "value": world * ncell * a.steps / dt, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
+        "e2e": {"value": world * ncell * a.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes)},
+        "gpu_launches": int(launches + launches_e2e),
+        "kernel_ms_per_step": kernel_ms / a.steps,   # CUDA events around k_integrate on its stream (max over ranks)
+        "roofline": roof, "fp64": fp64, "cpu_baseline": cpu, "parity": parity,
+        "solver": {"steps_per_model": S["nst"] / ncell, "lu_per_model": S["nlu"] / ncell,
+                   "jac_per_model": S["nje"] / ncell, "newton_iters_per_model": S["nni"] / ncell,
+                   "failed_dvode_calls": S["nfailcall"]},
+    }
 
 
 def main():
@@ -179,22 +228,26 @@ def main():
         if rank != 0:
             return
         cores = cpu_cores()
-        for w in range(a.warmup):
-            run_oracle_sample(params, cores, offset=w)
-        t0 = time.perf_counter()
-        n = 0
+        deadline = 120.0
+        for w in range(a.warmup):   # results discarded: a short bound is enough to page the library in
+            log(f"reference arm: warm-up sample {w + 1}/{a.warmup} on {cores} cores")
+            run_oracle_sample(params, cores, offset=1 + w, deadline_s=30.0)
+        n_done, dt, cut = 0, 0.0, 0
         for k in range(a.steps):
-            _, _, idx, _, flag = run_oracle_sample(params, cores, offset=100 + k)
-            n += len(idx)
-        dt = time.perf_counter() - t0
-        v = n / dt
-        sample = f"{cores} evenly spaced cells of the workload per step, one per host core"
+            v_k, dt_k, idx, _, flag = run_oracle_sample(params, cores, offset=100 + k, deadline_s=deadline)
+            n_done += int((flag != -98).sum())
+            cut += int((flag == -98).sum())
+            dt += dt_k
+            log(f"reference arm: step {k + 1}/{a.steps}: {dt_k:.1f} s, {int((flag != -98).sum())} of {len(idx)} cells finished")
+        v = n_done / dt
+        sample = (f"{cores} evenly spaced cells of the workload per step, one per host core, bounded at {deadline:.0f} s "
+                  f"per step ({cut} cells cut off and not counted)")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -285,51 +338,39 @@ def main():
         # ---- algorithmic work: solver counters x per-operation counts emitted by the generator
         flop = (C.c_double * 8)()
         lib.lib.uclgpu_work_model(flop)
-        f_rhs, f_jac, f_lu, f_solve, f_rates, b_interval = list(flop)[:6]
-        S = {k: stats[:, i].astype(np.float64).sum() for i, k in enumerate(STAT_FIELDS)}
-        w_flop = (S["nfe"] * f_rhs + S["nje"] * f_jac + S["nlu"] * f_lu + S["nni"] * f_solve +
-                  S["nintervals"] * f_rates)
-        w_bytes = S["nintervals"] * b_interval
-        kern_s = kernel_ms / 1e3 / a.steps          # one launch per step
-        peak, how = peak_hbm()
         pk = C.c_double(0.0)
         lib.lib.uclgpu_fp64_peak(local_rank, C.byref(pk))
-        traffic = None   # DRAM bytes of one k_integrate launch of this workload, from the committed ncu capture
+        traffic = None   # DRAM bytes of one k_integrate launch of this workload, from the committed ncu launch list
         tf = ROOT / "profiles" / "traffic.json"
         if tf.exists() and not a.cells and not a.full_grid:
             traffic = json.loads(tf.read_text()).get("k_integrate_dram_bytes_per_launch")
-        roof = {"bound": "hbm", "achieved": w_bytes / kern_s / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": w_bytes / kern_s / 1e9 / peak, "traffic": traffic, "peak_source": how,
-                "note": "state is chip-resident per cell: HBM traffic is only cell load/store, the kernel is bound "
-                        "by shared-memory/L2 latency and the fp64 pipe, see fp64"}
-        fp64 = {"achieved_tflops": w_flop / kern_s / 1e12, "peak_tflops": pk.value,
-                "frac": w_flop / kern_s / 1e12 / pk.value if pk.value else None,
-                "peak_source": "DFMA micro-benchmark run by this process (uclgpu_fp64_peak)"}
         cores = cpu_cores()
-        log(f"cpu_baseline: oracle on {cores} cores")
-        cv, cdt, idx, yref, cflag = run_oracle_sample(params, cores)
-        log(f"cpu_baseline: {cdt:.1f} s")
-        y_gpu = h_y.numpy()[idx][:, :335]
-        m = yref[:, :335] > 1e-15
-        dex = float(np.abs(np.log10(y_gpu[m] / yref[:, :335][m])).max())
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(params.nbytes),
-                    "d2h_bytes_per_step": int(h_y.numel() * 8 + h_phys.numel() * 8 + h_flag.numel() * 4 +
-                                              h_stats.numel() * 8)},
-            "gpu_launches": int(launches + launches_e2e),
-            "roofline": roof, "fp64": fp64,
-            "cpu_baseline": {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{len(idx)} evenly spaced cells of the workload, one per host core, {cdt:.1f} s"},
-            "parity": {"max_dex_vs_oracle_on_sample": dex, "flags_nonzero": int((flags != 0).sum()),
-                       "oracle_flags_nonzero": int((cflag != 0).sum())},
-            "solver": {"steps_per_model": S["nst"] / ncell, "lu_per_model": S["nlu"] / ncell,
-                       "jac_per_model": S["nje"] / ncell, "newton_iters_per_model": S["nni"] / ncell,
-                       "failed_dvode_calls": S["nfailcall"]},
-        }
-        print(json.dumps(line))
+        deadline = 120.0
+        log(f"cpu_baseline: oracle on {cores} cores, bounded at {deadline:.0f} s")
+        try:
+            cv, cdt, idx, yref, cflag = run_oracle_sample(params, cores, deadline_s=deadline)
+            ok = cflag == 0
+            y_gpu = h_y.numpy()[idx][:, :335]
+            m = (yref[:, :335] > 1e-15) & ok[:, None]
+            dex = float(np.abs(np.log10(y_gpu[m] / yref[:, :335][m])).max()) if m.any() else None
+            cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": sample_text(idx, cflag, cdt, deadline)}
+            parity = {"max_dex_vs_oracle_on_sample": dex, "sample_cells_compared": int(ok.sum()),
+                      "flags_nonzero": int((flags != 0).sum()),
+                      "oracle_flags_nonzero": int(((cflag != 0) & (cflag != -98)).sum())}
+            log(f"cpu_baseline: {cdt:.1f} s, {cv:.3f} models/s")
+        except Exception as e:   # the GPU numbers must not be lost to a CPU-side problem
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {e!r}"}
+            parity = {"flags_nonzero": int((flags != 0).sum())}
+        # the timed numbers first, on stderr, in case anything below goes wrong
+        log(f"value {value:.2f} {UNIT}, e2e {e2e_value:.2f} {UNIT}, kernel {kernel_ms / a.steps:.1f} ms/step")
+        line = assemble_line(a=a, world=world, ncell=ncell, workload=workload, dt=dt, kernel_ms=kernel_ms,
+                             dt_e2e=dt_e2e, launches=launches, launches_e2e=launches_e2e, stats=stats, flags=flags,
+                             clocks=clocks, work_model=list(flop), fp64_peak_tflops=pk.value,
+                             h2d_bytes=params.nbytes,
+                             d2h_bytes=h_y.numel() * 8 + h_phys.numel() * 8 + h_flag.numel() * 4 + h_stats.numel() * 8,
+                             cpu=cpu, parity=parity, traffic=traffic, stat_fields=STAT_FIELDS)
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -81,6 +81,15 @@ class Oracle:
         L.orc_h2_photo_diss_rate.argtypes = [C.c_double] * 4
         L.orc_co_photo_diss_rate.restype = C.c_double
         L.orc_co_photo_diss_rate.argtypes = [C.c_double] * 4
+        L.orc_set_deadline.restype = None
+        L.orc_set_deadline.argtypes = [C.c_double]
+
+    FLAG_DEADLINE = -98
+
+    def set_deadline(self, seconds: float) -> None:
+        """Benchmark guard (not reference behaviour): models still running `seconds` from now stop with
+        FLAG_DEADLINE; 0 switches the guard off."""
+        self.lib.orc_set_deadline(float(seconds))
 
     # ------------------------------------------------------------------
     def _arr(self, a, dtype):

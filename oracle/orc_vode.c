@@ -11,6 +11,7 @@
  *   DGEFA/DGESL :11982-12204 (LINPACK LU with partial pivoting)
  * Constants: dvode.f90:1875-1911.
  */
+#define _POSIX_C_SOURCE 200809L /* clock_gettime for the benchmark wall-clock guard */
 #include "orc_vode.h"
 
 #include <float.h>
@@ -18,6 +19,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #define ADDON 1.0e-6
 #define BIAS1 6.0
@@ -711,7 +713,7 @@ int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double to
     for (;;) {
         if (!first) {
             /* label 200 */
-            if (s->nst - nslast >= mxstep) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -1; }
+            if (s->nst - nslast >= mxstep || orc_deadline_expired()) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -1; }
             if (ewset(s, YH(1)) != 0) { memcpy(y, YH(1), n * sizeof(double)); *t = s->tn; return -6; }
         }
         first = 0;
@@ -733,3 +735,14 @@ int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double to
         return 2;
     }
 }
+
+/* ---- wall-clock guard for bounded benchmark samples (see orc_vode.h) ---------------------------- */
+static volatile double g_deadline = 0.0;
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+void orc_set_deadline(double seconds_from_now) { g_deadline = seconds_from_now > 0.0 ? now_s() + seconds_from_now : 0.0; }
+int orc_deadline_expired(void) { return g_deadline > 0.0 && now_s() > g_deadline; }

@@ -27,4 +27,11 @@ void vode_free(vode_t *s);
 int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double tout, double rtol,
                const double *atol, int mxstep);
 
+/* Wall-clock guard for bounded benchmark samples (NOT part of the reference algorithm): after
+ * orc_set_deadline(seconds) every model still running `seconds` from now stops with
+ * ORC_FLAG_DEADLINE.  0 switches the guard off (default). */
+#define ORC_FLAG_DEADLINE (-98)
+void orc_set_deadline(double seconds_from_now);
+int orc_deadline_expired(void);
+
 #endif

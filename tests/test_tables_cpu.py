@@ -150,3 +150,57 @@ def test_network_json_matches_reference_network_f90(net):
     for k in ("alpha", "beta", "gama", "re", "pr", "mass", "binding_energy", "min_temps", "max_temps", "rtype"):
         assert np.array_equal(getattr(fresh, k), getattr(net, k)), k
     assert fresh.names == net.names
+
+
+def _emit_units(name, programs, **kw):
+    """Run the emitter on a list of level programs and parse the unit table back."""
+    import re
+    from uclchem_b200.makerates_cuda import _emit_program
+    out = []
+    _emit_program(out.append, name, programs, **kw)
+    text = "".join(out)
+    body = re.search(name + r"_units\[\d+\] = \{([^}]*)\}", text).group(1)
+    u = np.array([int(x.strip().rstrip("u")) for x in body.split(",") if x.strip()], dtype=np.uint64).reshape(-1, 2)
+    nterms = int(re.search(name + r"_terms\[(\d+)\]", text).group(1))
+    return u, nterms, text
+
+
+def test_unit_tables_sync_flags_and_padding(gen):
+    """Unit tables: block barrier after every level, except a warp-level sync where this level and the
+    next both fit into the 32 slots of warp 0; term tables padded for the unconditional batch loads."""
+    from uclchem_b200.makerates_cuda import TERM_PAD, NTHREADS
+    progs = gen.fwd + [gen.tail]
+    u, nterms, text = _emit_units("net_fwd", progs, warp_chains=True)
+    assert "__constant__" in text.split("net_fwd_units")[0].splitlines()[-1]
+    assert nterms == sum(len(p.terms) for p in progs) + TERM_PAD and TERM_PAD >= 32 * 8
+    k = 0
+    for lev, p in enumerate(progs):
+        npass = max(1, -(-p.nslots // NTHREADS))
+        for i in range(npass):
+            first, word = int(u[k, 0]), int(u[k, 1])
+            end, sync = word & 0x3FFFFFFF, word >> 30
+            assert end - first <= p.nslots and first % 32 == 0
+            if i < npass - 1:
+                assert sync == 0
+            else:
+                local = lev + 1 < len(progs) and p.nslots <= 32 and progs[lev + 1].nslots <= 32
+                assert sync == (1 if local else 2)
+            k += 1
+    assert k == len(u)
+    # without the option every level ends with a block barrier
+    u2, _, _ = _emit_units("net_x", progs)
+    assert all((int(w) >> 30) in (0, 2) for w in u2[:, 1])
+    # the gather runs on the 14 worker warps of rhs_eval: passes of NTHREADS - 64 slots
+    ug, _, _ = _emit_units("net_gather", [gen.gather], term16=True, nthreads=NTHREADS - 64)
+    assert list(ug[:, 0]) == list(range(0, gen.gather.nslots, NTHREADS - 64))
+
+
+def test_deferred_photo_reactions(gen, net):
+    """H2 + hv and CO + hv: unimolecular, gas-phase rows only, absent from flux table and gather terms."""
+    assert len(gen.deferred) == 2
+    used = {int(t) & 0x7FFF for t in gen.gather.terms}
+    for r in gen.deferred:
+        assert r not in used and r not in set(int(x) for x in gen.flux_tab[:, 0] & 0xFFFF)
+        rows = gen.deferred_rows[r]
+        assert 1 <= len(rows) <= 4 and sum(sg for _, sg in rows) == 1   # A -> B + C
+        assert all(i < net.nspec and net.names[i][0] not in "#@" for i, _ in rows)
