@@ -34,18 +34,27 @@ def generate(tag: str = "default", network_f90: str | None = None) -> Path:
     return emit(Generated(net), CSRC / "generated" / tag, tag)
 
 
-def compile(tag: str = "default", force: bool = False, verbose: bool = False) -> Path:
+# build variants: suffix of the library name -> extra nvcc defines
+VARIANTS = {
+    "": [],
+    # product-form triangular solves (product_form.py): CPU-validated, to be A/B-tested on a B200
+    # (`python tools/gpu_ab.py default default_pf 592`) before it becomes the default
+    "pf": ["-DUCLGPU_PRODUCT_FORM"],
+}
+
+
+def compile(tag: str = "default", force: bool = False, verbose: bool = False, variant: str = "") -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     gen = CSRC / "generated" / tag / "net_tables.cuh"
     if not gen.exists():
         generate(tag)
     LIBDIR.mkdir(exist_ok=True)
-    out = LIBDIR / f"libuclgpu_{tag}.so"
+    out = LIBDIR / (f"libuclgpu_{tag}_{variant}.so" if variant else f"libuclgpu_{tag}.so")
     srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_bdf.cuh",
             CSRC / "engine_model.cuh", gen, _PKG.parent / "include" / "uclgpu.h"]
     if not force and out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return out
-    cmd = [nvcc, *NVCC_FLAGS, f"-I{gen.parent}", "-o", str(out), str(CSRC / "uclgpu.cu")]
+    cmd = [nvcc, *NVCC_FLAGS, *VARIANTS[variant], f"-I{gen.parent}", "-o", str(out), str(CSRC / "uclgpu.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -341,7 +341,7 @@ __device__ __noinline__ void vnls_dev(Smem &s, Blk &b)
             lin_solve(s);
             double d = 0.0;
             if (tid < NEQ) {
-                d = s.xs[net_iperm[tid]];
+                d = SOLVE_RESULT(s)[net_iperm[tid]];
                 if (dump) b.dump[5 * NEQ + tid] = d;
                 if (fabs(st.rc - 1.0) > 0.0) d *= 2.0 / (1.0 + st.rc);
             }

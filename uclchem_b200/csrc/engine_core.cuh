@@ -87,8 +87,20 @@ struct Scalars {
     double dbg[64];
 };
 
+// Product-form solves (uclchem_b200/product_form.py): with -DUCLGPU_PRODUCT_FORM
+// factor_p also forms the explicit sparse inverses of the factors of the sparse pivots (in place +
+// NET_NVAL_PF - NET_NVAL fill slots) and lin_solve is five wide levels; the result is left in s.tmpv.
+// CPU-validated (tests/test_product_form_cpu.py); not the default until it has been run on a B200.
+#ifdef UCLGPU_PRODUCT_FORM
+#define NET_NVAL_STORE NET_NVAL_PF
+#define SOLVE_RESULT(s) ((s).tmpv)
+#else
+#define NET_NVAL_STORE NET_NVAL
+#define SOLVE_RESULT(s) ((s).xs)
+#endif
+
 struct __align__(16) Smem {
-    double val[(NET_NVAL + 7) & ~7];
+    double val[(NET_NVAL_STORE + 7) & ~7];
     double rate[(NREAC + 7) & ~7];
     double flux[(NREAC + 7) & ~7];
     double y[NEQP + 8];        // iterate + ext slots y[NEQ+0..3] = {1, blr, 1/safeMantle, tau}

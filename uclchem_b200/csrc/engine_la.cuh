@@ -512,6 +512,25 @@ __device__ __noinline__ bool factor_p(Smem &s, Blk &b)
         });
     TIMER_ADD(cyc_factor)
     bool ok = dense_inverse(s);
+#ifdef UCLGPU_PRODUCT_FORM
+    {
+        // X = inv(L11), Y = inv(U11) on their closure patterns: level programs into the staging buffer
+        // (the flux array: dead outside rhs_eval), then one copy into the final positions -- entries that
+        // exist in L11 / U11 are overwritten (not needed any more), fill entries go to the extra slots.
+        static_assert(NET_PF_NSTG <= NREAC, "staging buffer is the flux array");
+        double *stg = s.flux;
+        if (tid < NET_N0) stg[NET_PF_DIAG0 + tid] = val[net_diag_pos[tid]];
+        if (tid == 0) stg[NET_PF_ONE] = 1.0;
+        BLOCK_SYNC();
+        run_levels<4>(
+            net_pf_inv_desc, net_pf_inv_terms, net_pf_inv_units, NET_PF_INV_NUNITS,
+            [&](uint32_t t) { return make_double2(val[t >> 16], stg[t & 0xFFFFu]); },
+            [](uint32_t target) { return (uint32_t)__ldg(net_pf_inv_scale + target); },
+            [&](uint32_t target, double acc, uint32_t sc) { stg[target] = -stg[sc] * acc; });
+        for (int i = tid; i < NET_PF_NX + NET_PF_NY; i += NT) val[net_pf_final_pos[i]] = stg[i];
+        BLOCK_SYNC();
+    }
+#endif
     double bad = 0.0;
     if (tid < NET_N0) {
         double d = val[net_diag_pos[tid]];
@@ -523,6 +542,54 @@ __device__ __noinline__ bool factor_p(Smem &s, Blk &b)
     return ok && bad == 0.0;
 }
 
+#ifdef UCLGPU_PRODUCT_FORM
+// Solve P x = b, product form.  s.xs holds b in elimination order (block-visible); on return
+// s.tmpv = x (SOLVE_RESULT).  Five levels: y1 = b1 + X b1 | b2' = b2 - L21 y1 | x2 = Tinv b2' |
+// w = y1 - U12 x2 | x1 = Y w; xs and tmpv alternate as source and destination so no level
+// reads what it writes.
+__device__ __noinline__ void lin_solve(Smem &s)
+{
+    const int tid = threadIdx.x;
+    const double *val = s.val;
+    double *xs = s.xs, *tv = s.tmpv;
+    TIMER_START
+    run_levels<4>(
+        net_pf_p1_desc, net_pf_p1_terms, net_pf_p1_units, NET_PF_P1_NUNITS,
+        [&](uint32_t t) { return make_double2(val[t >> 16], xs[t & 0xFFFFu]); },
+        [](uint32_t) { return 0u; },
+        [&](uint32_t target, double acc, uint32_t) { tv[target] = xs[target] + acc; });
+    run_levels<4>(
+        net_pf_tail_desc, net_pf_tail_terms, net_pf_tail_units, NET_PF_TAIL_NUNITS,
+        [&](uint32_t t) { return make_double2(val[t >> 16], tv[t & 0xFFFFu]); },
+        [](uint32_t) { return 0u; },
+        [&](uint32_t target, double acc, uint32_t) { xs[target] -= acc; });
+    {
+        // x_T = Tinv * b_T : 4 lanes per row, straight into tmpv[n0..]
+        const double *T = val + NET_OFF_DENSE;
+        int row = tid >> 2, sub = tid & 3;
+        double acc = 0.0;
+        if (row < MDENSE) {
+#pragma unroll 4
+            for (int j = sub; j < MDENSE; j += 4) acc += T[row * MDENSE + j] * xs[NET_N0 + j];
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        if (row < MDENSE && sub == 0) tv[NET_N0 + row] = acc;
+    }
+    BLOCK_SYNC();
+    run_levels<4>(
+        net_pf_p4_desc, net_pf_p4_terms, net_pf_p4_units, NET_PF_P4_NUNITS,
+        [&](uint32_t t) { return make_double2(val[t >> 16], tv[t & 0xFFFFu]); },
+        [](uint32_t) { return 0u; },
+        [&](uint32_t target, double acc, uint32_t) { xs[target] = tv[target] - acc; });
+    run_levels<4>(
+        net_pf_p5_desc, net_pf_p5_terms, net_pf_p5_units, NET_PF_P5_NUNITS,
+        [&](uint32_t t) { return make_double2(val[t >> 16], xs[t & 0xFFFFu]); },
+        [](uint32_t) { return 0u; },
+        [&](uint32_t target, double acc, uint32_t) { tv[target] = acc; });
+    TIMER_ADD(cyc_solve)
+}
+#else
 // Solve P x = b.  s.xs holds b in elimination order (block-visible); on return s.xs = x.
 __device__ __noinline__ void lin_solve(Smem &s)
 {
@@ -559,3 +626,4 @@ __device__ __noinline__ void lin_solve(Smem &s)
         [&](uint32_t target, double acc, uint32_t) { xs[target] = (xs[target] - acc) * s.invd[target]; });
     TIMER_ADD(cyc_solve)
 }
+#endif // UCLGPU_PRODUCT_FORM

@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         BLOCK_SYNC();
         constraint_rhs(s);
         lin_solve(s);
-        for (int i = tid; i < NAUG; i += NT) a.out[(size_t)cell * NAUG + i] = ok ? s.xs[net_iperm[i]] : nan("");
+        for (int i = tid; i < NAUG; i += NT) a.out[(size_t)cell * NAUG + i] = ok ? SOLVE_RESULT(s)[net_iperm[i]] : nan("");
     }
 }
 

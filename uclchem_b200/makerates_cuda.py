@@ -31,7 +31,7 @@ from pathlib import Path
 
 import numpy as np
 
-from . import symbolic
+from . import product_form, symbolic
 from .network import N_EXT, TYPE_ID, TYPE_NAMES, Network
 
 NTHREADS = 512
@@ -190,6 +190,20 @@ class Generated:
             a, b = sym.tail_l_ptr[t], sym.tail_l_ptr[t + 1]
             items.append((sym.n0 + t, [(int(p) << 16) | int(c) for p, c in zip(sym.tail_l_pos[a:b], sym.tail_l_col[a:b])]))
         self.tail = TeamProgram(items, terms_per_lane=8)
+        # product-form solves (product_form.py): inverse program + the three new solve levels
+        self.pf = pf = product_form.build(sym)
+        pk = lambda terms: [(int(p) << 16) | int(k) for p, k in terms]
+        self.pf_inv = [TeamProgram([(t, pk(terms)) for t, _, terms in lv], terms_per_lane=SOLVE_TERMS_PER_LANE)
+                       for lv in pf.inv_levels]
+        scale = np.full(pf.nstg, 0xFFFF, np.int64)
+        for lv in pf.inv_levels:
+            for t, sc, _ in lv:
+                scale[t] = sc
+        self.pf_inv_scale = scale
+        self.pf_p1 = TeamProgram([(i, pk(t)) for i, t in pf.p1], terms_per_lane=SOLVE_TERMS_PER_LANE)
+        self.pf_p4 = TeamProgram([(i, pk(t)) for i, t in pf.p4], terms_per_lane=SOLVE_TERMS_PER_LANE)
+        self.pf_p5 = TeamProgram([(i, pk(t)) for i, t in pf.p5], terms_per_lane=SOLVE_TERMS_PER_LANE)
+        self.pf_tail = TeamProgram(items, terms_per_lane=SOLVE_TERMS_PER_LANE)
 
     # scaling map for factor targets: diag position or -1
     def factor_diag_table(self):
@@ -485,6 +499,18 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     w(_c_array("net_factor_diag", gen.factor_diag_table(), "uint16_t"))
     _emit_program(w, "net_fwd", gen.fwd + [gen.tail], warp_chains=True)  # forward levels, then b_T -= L21 x
     _emit_program(w, "net_bwd", gen.bwd, warp_chains=True)
+    w("\n// ---- product-form solves (product_form.py; device side behind -DUCLGPU_PRODUCT_FORM) ----------\n")
+    pf = gen.pf
+    w(f"#define NET_NVAL_PF {pf.nval_pf}\n#define NET_PF_NX {pf.nx}\n#define NET_PF_NY {pf.ny}\n")
+    w(f"#define NET_PF_DIAG0 {pf.stg_diag0}\n#define NET_PF_ONE {pf.stg_one}\n#define NET_PF_NSTG {pf.nstg}\n")
+    assert pf.nstg <= net.nreac, "the staging buffer of the inverse program is the flux array"
+    _emit_program(w, "net_pf_inv", gen.pf_inv)
+    w(_c_array("net_pf_inv_scale", gen.pf_inv_scale, "uint16_t"))
+    w(_c_array("net_pf_final_pos", pf.final_pos, "uint16_t"))
+    _emit_program(w, "net_pf_p1", [gen.pf_p1])
+    _emit_program(w, "net_pf_tail", [gen.pf_tail])
+    _emit_program(w, "net_pf_p4", [gen.pf_p4])
+    _emit_program(w, "net_pf_p5", [gen.pf_p5])
     w(_c_array("net_perm", sym.perm, "uint16_t"))
     w(_c_array("net_iperm", sym.iperm, "uint16_t"))
     path = outdir / "net_tables.cuh"
