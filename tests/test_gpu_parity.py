@@ -202,3 +202,22 @@ def test_model_api_mirrors_reference(lib, net):
     assert flag2 == 0 and np.allclose(chem2[0, 0], start)
     g = model.cloud_grid({"initialDens": [1e3, 1e4, 1e5], "finalTime": 1e2}, out_species=["CO"])
     assert g["abundances"].shape == (3, 335) and (g["flag"] == 0).all()
+
+
+def test_disk_mode_files(lib, net, tmp_path):
+    """The reference's disk mode (io.f90 formats, uclchem_b200/datio.py): outputFile / abundSaveFile are
+    written after the run, abundLoadFile seeds the next one."""
+    from uclchem_b200 import datio
+    pd_ = {"initialDens": 1e4, "initialTemp": 10.0, "finalTime": 1e3}
+    full, save = tmp_path / "full.dat", tmp_path / "final.dat"
+    res = model.cloud(param_dict={**pd_, "outputFile": str(full), "abundSaveFile": str(save)}, out_species=["CO"])
+    assert res[0] == 0 and res[1] > 0
+    phys, chem, _, start, flag = model.cloud(param_dict=pd_, return_array=True)
+    names, data = datio.read_output_file(full)
+    assert names[8:] == net.names and data.shape == (phys.shape[0], 8 + net.nspec)
+    assert np.allclose(data[:, 8:], chem[:, 0, :], rtol=1e-5, atol=0) and np.allclose(data[:, 0], phys[:, 0, 0], rtol=1e-3)
+    final = datio.read_abundances(save, net.nspec)
+    assert np.allclose(final, start, rtol=1e-5, atol=0)
+    res2 = model.cloud(param_dict={**pd_, "finalTime": 1e2, "abundLoadFile": str(save), "outputFile": str(full)})
+    _, data2 = datio.read_output_file(full)
+    assert res2[0] == 0 and np.allclose(data2[0, 8:], final, rtol=1e-5, atol=0)

@@ -9,8 +9,11 @@ reference leaves to user scripts (``scripts/grid.py:41-59``): ``cloud_grid``,
 
 Differences from the reference, all deliberate:
 
-* file based I/O (``outputFile``, ``abundSaveFile`` ...) is not part of the hot path
-  and is refused with the reference's own error; use the in-memory modes;
+* file based I/O is done on the host after the run (``datio.py``): ``outputFile`` (full output,
+  ``io.f90`` formats 335/8020), ``abundSaveFile`` / ``abundLoadFile`` (format 8010) are honoured in the
+  reference's disk mode (neither ``return_array`` nor ``return_dataframe``); ``columnFile``,
+  ``rateFile`` and ``fluxFile`` are not written; combining file keys with the in-memory modes is
+  refused with the reference's own error (``model.py:121-131``);
 * parameters start from ``defaultparameters.f90`` on every call (the reference leaks
   parameters between calls, SURVEY.md Q6);
 * a model failure is reported through the success flag, never raised
@@ -20,6 +23,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import datio
 from ._capi import N_PHYS, get_library
 from .params import MODEL_KINDS, params_from_dict
 
@@ -36,19 +40,21 @@ def _lower(param_dict):
 
 
 def pre_flight_checklist(return_array, return_dataframe, return_rates, starting_chemistry=None, user_params=None):
-    """model.py:103-155, minus the disk mode (which this path does not offer)."""
+    """model.py:103-155: in-memory and disk modes are not mixed.  (The reference also forbids switching
+    mode within one Python session -- an artefact of its SAVEd Fortran file units; not needed here.)"""
     user_params = user_params or {}
     if starting_chemistry is not None:
         assert return_array or return_dataframe, (
             "starting_chemistry can only be used with return_array or return_dataframe set to True;\n"
             "Instead specify 'abundLoadFile' in the param_dict to load starting abundances from a file.")
-    file_keys = [k for k in user_params if k.lower().endswith("file")]
-    if file_keys:
-        raise RuntimeError("return_array or return_dataframe cannot be used if any output of input file is "
-                           "specified.\n" + f"Offending keys: {', '.join(file_keys)}")
-    if return_rates:
-        assert return_array or return_dataframe, (
-            "return_rates and return_heating can only be used with return_array or return_dataframe set to True; ")
+    if return_array or return_dataframe or return_rates:
+        file_keys = [k for k in user_params if k.lower().endswith("file")]
+        if file_keys:
+            raise RuntimeError("return_array or return_dataframe cannot be used if any output of input file is "
+                               "specified.\n" + f"Offending keys: {', '.join(file_keys)}")
+        if return_rates:
+            assert return_array or return_dataframe, (
+                "return_rates and return_heating can only be used with return_array or return_dataframe set to True; ")
 
 
 def _format_output(n_out, abunds, success_flag):
@@ -61,7 +67,13 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
                 timepoints, extra):
     lib = get_library()
     pd_ = _lower(param_dict)
+    traj = return_array or return_dataframe
     pre_flight_checklist(return_array, return_dataframe, return_rates, starting_chemistry, pd_)
+    # disk mode of the reference: files named in the dictionary are read before / written after the run
+    files = {k: pd_.pop(k) for k in list(pd_) if k.endswith("file")}
+    for k in ("columnfile", "ratefile", "fluxfile"):
+        if k in files:
+            raise NotImplementedError(f"{k} is not written by the GPU path; use return_array / return_dataframe")
     pd_.update(extra)
     params = params_from_dict(pd_, ncell=1)
     y0 = None
@@ -69,11 +81,20 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
         sc = np.asarray(starting_chemistry, dtype=np.float64).ravel()
         y0 = np.zeros((1, lib.neq))
         y0[0, : lib.nspec] = sc[: lib.nspec]
-    traj = return_array or return_dataframe
-    out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if traj else 0,
-                       want_physics=traj, want_chem=traj, want_rates=traj and return_rates)
+    elif "abundloadfile" in files:          # readInputAbunds, io.f90:36-46
+        y0 = np.zeros((1, lib.neq))
+        y0[0, : lib.nspec] = datio.read_abundances(files["abundloadfile"], lib.nspec)
+    want_rows = traj or "outputfile" in files
+    out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if want_rows else 0,
+                       want_physics=want_rows, want_chem=want_rows, want_rates=traj and return_rates)
     flag = int(out["flag"][0])
     if not traj:
+        if "outputfile" in files:
+            nrows = min(int(out["stats"][0][7]) + 1, timepoints + 1)
+            datio.write_full_output(files["outputfile"], lib.species, out["physics"][0, :nrows],
+                                    out["abund"][0, :nrows])
+        if "abundsavefile" in files:          # finalOutput, io.f90:48-56
+            datio.write_abundances(files["abundsavefile"], out["y_final"][0, : lib.nspec])
         n_out = len(out_species) if out_species else 0
         idx = [lib.species.index(s) for s in (out_species or [])]
         res = _format_output(n_out, out["y_final"][0, idx], flag)
