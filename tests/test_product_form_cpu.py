@@ -112,3 +112,60 @@ def test_generated_programs_with_device_buffer_discipline(gen, eng, case, gamma)
     A = eng.to_dense(eng.assemble(y, rate, gamma))
     r = A @ x[sym.perm] - b[sym.perm]
     assert np.abs(r).max() <= 1e-6 * np.abs(b).max()
+
+
+def _items(prog):
+    """(target, [terms]) of every real team of a TeamProgram, decoded from its descriptor table."""
+    d = prog.desc
+    out = []
+    for s in range(prog.nslots):
+        begin, w = int(d[s, 0]), int(d[s, 1])
+        target, n, tl = w & 0xFFFF, (w >> 16) & 0xFFF, (w >> 28) & 7
+        if target != 0xFFFF and (s & ((1 << tl) - 1)) == 0:
+            out.append((target, [int(t) for t in prog.terms[begin: begin + n]]))
+    return out
+
+
+def test_levels_are_race_free(gen):
+    """Inside one level (everything between two block barriers) no item may read a location another
+    item of the same level writes.  Checked on the emitted programs for the buffer roles the device
+    uses: factor (val -> val in place), forward / backward substitution (xs in place), the inverse
+    program (val, stg -> stg) and the five product-form solve levels (xs <-> tmpv)."""
+    sym, pf = gen.sym, gen.pf
+    # factorisation: reads val[l], val[u], val[diag]; writes val[target]
+    diag = gen.factor_diag_table()
+    for prog, _ in gen.factor:
+        items = _items(prog)
+        writes = {t for t, _ in items}
+        for t, terms in items:
+            reads = {x >> 16 for x in terms} | {x & 0xFFFF for x in terms}
+            if diag[t] < 0xFFFE:
+                reads.add(int(diag[t]))
+            assert not (reads & (writes - {t}))
+    # substitutions: reads xs[col]; writes xs[target]
+    for prog in gen.fwd + [gen.tail] + gen.bwd:
+        items = _items(prog)
+        writes = {t for t, _ in items}
+        for t, terms in items:
+            assert not ({x & 0xFFFF for x in terms} & (writes - {t}))
+    # inverse program: reads val (never written here) and stg; writes stg[target]; scale read from stg
+    written_before = set(range(pf.stg_diag0, pf.nstg))            # diagonal copies + ONE, staged up front
+    for prog in gen.pf_inv:
+        items = _items(prog)
+        writes = {t for t, _ in items}
+        for t, terms in items:
+            reads = {x & 0xFFFF for x in terms} | {int(gen.pf_inv_scale[t])}
+            assert not (reads & writes)                          # nothing of this level is read in it
+            assert reads <= written_before                       # everything read was produced earlier
+            assert all((x >> 16) < sym.nval for x in terms)      # factor entries only, no fill slot
+        written_before |= writes
+    assert written_before >= set(range(pf.nx + pf.ny))           # every X / Y entry is produced
+    # product-form solve: each level reads one vector and writes the other
+    n0 = sym.n0
+    for prog, rd_lo, rd_hi, wr_lo, wr_hi in ((gen.pf_p1, 0, n0, 0, n0), (gen.pf_tail, 0, n0, n0, sym.naug),
+                                             (gen.pf_p4, n0, sym.naug, 0, n0), (gen.pf_p5, 0, n0, 0, n0)):
+        items = _items(prog)
+        assert sorted(t for t, _ in items) == list(range(wr_lo, wr_hi))     # every row of the block is written once
+        for t, terms in items:
+            assert all(rd_lo <= (x & 0xFFFF) < rd_hi for x in terms)
+            assert all((x >> 16) < pf.nval_pf for x in terms)

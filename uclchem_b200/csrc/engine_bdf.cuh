@@ -45,6 +45,83 @@
 #define T0_BEGIN BLOCK_SYNC(); if (threadIdx.x == 0) {
 #define T0_END } BLOCK_SYNC();
 
+#ifdef UCLGPU_VSET_REG
+// DVSET dvode.f90:7616 (BDF branch :7739-7786); thread 0 only. 1-based arrays.  Build variant
+// (-DUCLGPU_VSET_REG, not yet run on a B200): this runs on one thread while the rest of the CTA waits,
+// so the EL recurrences are unrolled over the maximum order with predicates and el[] / tau[] stay in
+// registers (statement order and arithmetic are DVSET's) instead of round-tripping through shared
+// memory for every update.
+__device__ __noinline__ void vset_dev(Scalars &st)
+{
+    const int nq = st.nq, l = st.l;
+    const double flotl = (double)l;
+    const int nqm1 = nq - 1, nqm2 = nq - 2;
+    const double h = st.h;
+    double el[LMAXORD + 2], tau[LMAXORD + 1];
+#pragma unroll
+    for (int i = 1; i <= LMAXORD; i++) tau[i] = st.tau[i];
+#pragma unroll
+    for (int i = 0; i < LMAXORD + 2; i++) el[i] = 0.0; // EL(3..L) = 0; entries above L are never used
+    el[1] = 1.0;
+    el[2] = 1.0;
+    double alph0 = -1.0, ahatn0 = -1.0, hsum = h, rxi = 1.0, rxis = 1.0;
+    if (nq != 1) {
+#pragma unroll
+        for (int j = 1; j <= LMAXORD - 3; j++) { // j <= NQ-2, NQ <= 5
+            if (j <= nqm2) {
+                hsum += tau[j];
+                rxi = h / hsum;
+                const int jp1 = j + 1;
+                alph0 -= 1.0 / (double)jp1;
+#pragma unroll
+                for (int i = j + 2; i >= 2; i--) el[i] = el[i] + el[i - 1] * rxi;
+            }
+        }
+        alph0 -= 1.0 / (double)nq;
+        rxis = -el[2] - alph0;
+        double tnqm1 = tau[1];
+#pragma unroll
+        for (int i = 2; i <= LMAXORD - 2; i++)
+            if (i == nqm1) tnqm1 = tau[i];
+        hsum += tnqm1;
+        rxi = h / hsum;
+        ahatn0 = -el[2] - rxi;
+#pragma unroll
+        for (int i = LMAXORD; i >= 2; i--) // i = NQ+1 .. 2
+            if (i <= nq + 1) el[i] = el[i] + el[i - 1] * rxis;
+    }
+    double ell = el[2];
+#pragma unroll
+    for (int i = 3; i <= LMAXORD; i++)
+        if (i == l) ell = el[i];
+    double *tq = st.tq;
+    double t1 = 1.0 - ahatn0 + alph0;
+    double t2 = 1.0 + (double)nq * t1;
+    tq[2] = fabs(alph0 * t2 / t1);
+    tq[5] = fabs(t2 / (ell * rxi / rxis));
+    if (st.nqwait == 1) {
+        double cnqm1 = rxis / ell;
+        double t3 = alph0 + 1.0 / (double)nq;
+        double t4 = ahatn0 + rxi;
+        double elp = t3 / (1.0 - t4 + t3);
+        tq[1] = fabs(elp / cnqm1);
+        double tnq = tau[1];
+#pragma unroll
+        for (int i = 2; i <= LMAXORD - 1; i++)
+            if (i == nq) tnq = tau[i];
+        hsum += tnq;
+        rxi = h / hsum;
+        double t5 = alph0 - 1.0 / (double)(nq + 1);
+        double t6 = ahatn0 - rxi;
+        elp = t2 / (1.0 - t6 + t5);
+        tq[3] = fabs(elp * rxi * (flotl + 1.0) * t5);
+    }
+    tq[4] = V_CORTES * tq[2];
+#pragma unroll
+    for (int i = 1; i <= LMAXORD; i++)
+        if (i <= l) st.el[i] = el[i];
+}
+#else
 // DVSET dvode.f90:7616 (BDF branch :7739-7786); thread 0 only. 1-based arrays.
 __device__ __noinline__ void vset_dev(Scalars &st)
 {
@@ -96,6 +173,7 @@ __device__ __noinline__ void vset_dev(Scalars &st)
     }
     tq[4] = V_CORTES * tq[2];
 }
+#endif // UCLGPU_VSET_REG
 
 // DVJUST dvode.f90:7790 (BDF :7862-7921).  Ends with a barrier.
 __device__ __noinline__ void vjust_dev(Smem &s, int iord)
