@@ -99,3 +99,35 @@ def test_jacobian_lu_and_product_form(net2, gen2, cases, case, gamma):
     assert np.abs(x[:neq] - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
     xp = product_form.solve(gen2.pf, sym, product_form.invert(gen2.pf, sym, val), ba)
     assert np.abs(xp[:neq] - x_ref).max() <= 1e-7 * np.abs(x_ref).max()
+
+
+def test_oracle_runs_the_reference_photo_on_grain_static_model(net2):
+    """First model of tests/test_photo_on_grain.py:101-120 of the reference on this network: the static
+    cloud with the reference's own tolerances for this (stiffer) network, shortened from 5 Myr to 1 Myr
+    to keep the CPU suite short (the free-fall and hot-core stages of that test take minutes per model
+    on this network).  The reference asserts `return_code == 0` and nothing else; the budgets of the
+    elements every reaction conserves must also stay put."""
+    from oracle.oracle import Oracle
+    from uclchem_b200.params import params_from_dict
+    orc = Oracle(net2)
+    orc.set_deadline(120.0)
+    r = orc.run_model(0, params_from_dict({"endAtFinalDensity": False, "freefall": False, "initialDens": 1e4,
+                                           "initialTemp": 10.0, "finalDens": 1e5, "finalTime": 1.0e6,
+                                           "abstol_min": 1e-15, "reltol": 1e-5})[:, 0])
+    orc.set_deadline(0.0)
+    assert r["flag"] == 0 and r["physics"][-1, 0] == pytest.approx(1.0e6, rel=1e-6)
+    for e in ("C", "O", "N"):
+        w = np.array([_count(n, e) for n in net2.names[:333]], float)
+        a0, a1 = float(w @ r["abund"][0, :333]), float(w @ r["abund"][-1, :333])
+        assert a0 > 0 and abs(a1 - a0) <= 1e-6 * a0, (e, a0, a1)
+
+
+def _count(name, element):
+    """Atoms of `element` (one- or two-letter symbol) in a species name like '#CH3OH', 'HCO+', '@SIC2'."""
+    import re
+    s = name.lstrip("#@").rstrip("+-")
+    tot = 0
+    for sym, num in re.findall(r"(CL|MG|SI|HE|[A-Z])(\d*)", s):
+        if sym == element:
+            tot += int(num) if num else 1
+    return tot
