@@ -9,6 +9,7 @@
 set -x
 mkdir -p gpurun_out
 timeout 300 python tools/gpu_ab.py default default_pf 592 > gpurun_out/ab_pf_592.log 2>&1; cat gpurun_out/ab_pf_592.log
+timeout 200 python tools/gpu_ab.py default_pf default_pfo 592 > gpurun_out/ab_pfo_592.log 2>&1; cat gpurun_out/ab_pfo_592.log
 timeout 200 python tools/gpu_ab.py default default_vs 592 > gpurun_out/ab_vs_592.log 2>&1; cat gpurun_out/ab_vs_592.log
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -3 gpurun_out/pytest_gpu.log
 timeout 500 python bench.py --warmup 3 --steps 1 > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -8 gpurun_out/bench.err

@@ -40,6 +40,8 @@ VARIANTS = {
     # product-form triangular solves (product_form.py): CPU-validated, to be A/B-tested on a B200
     # (`python tools/gpu_ab.py default default_pf 592`) before it becomes the default
     "pf": ["-DUCLGPU_PRODUCT_FORM"],
+    # ... with the inverse program on the warps that idle during the dense Gauss-Jordan inverse
+    "pfo": ["-DUCLGPU_PRODUCT_FORM", "-DUCLGPU_PF_OVERLAP"],
     # DVSET with el[] / tau[] in registers (engine_bdf.cuh): same statements, not yet run on a B200
     "vs": ["-DUCLGPU_VSET_REG"],
 }

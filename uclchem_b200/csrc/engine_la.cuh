@@ -36,13 +36,17 @@ __device__ __forceinline__ double masked_fma(double a, double x, double acc, boo
     return acc;
 }
 
-template <int U, class TermT, class TermF, class PreF, class FinF>
+// GROUP = 0: the whole CTA runs the program (block barriers).  GROUP = g > 0: the g threads starting at
+// tid_base run it on their own (named barrier 2), e.g. the warps that idle during the dense inverse.
+template <int U, int GROUP = 0, class TermT, class TermF, class PreF, class FinF>
 __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, const TermT *__restrict__ terms,
-                                           const uint32_t *units, int nunits, TermF term, PreF pre, FinF fin)
+                                           const uint32_t *units, int nunits, TermF term, PreF pre, FinF fin,
+                                           uint32_t tid_base = 0u)
 {
     const uint2 *d2 = reinterpret_cast<const uint2 *>(desc);
     const uint2 *units2 = reinterpret_cast<const uint2 *>(units);
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t tid_rel = GROUP ? threadIdx.x - tid_base : threadIdx.x;
     auto fetch_desc = [&](int k) {
         TeamSlot t;
         t.d = make_uint2(0u, 0xFFFFu);
@@ -50,7 +54,7 @@ __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, co
         t.warp_on = false;
         if (k < nunits) {
             const uint2 un = units2[k];
-            t.sl = un.x + threadIdx.x;
+            t.sl = un.x + tid_rel;
             t.warp_on = t.sl - lane < (un.y & 0x3FFFFFFFu); // slot ranges are padded to multiples of 32
             if (t.warp_on) t.d = __ldg(d2 + t.sl);
         }
@@ -116,8 +120,10 @@ __device__ __forceinline__ void run_levels(const uint32_t *__restrict__ desc, co
             if (target != 0xFFFFu && lit == 0u) fin(target, acc, aux);
         }
         const uint32_t sync = units2[k].y >> 30; // 2: block barrier, 1: the next level also lives in warp 0
-        if (sync & 2u) BLOCK_SYNC();
-        else if (sync) __syncwarp();
+        if (sync & 2u) {
+            if (GROUP) asm volatile("barrier.sync 2, %0;" ::"n"(GROUP ? GROUP : 32) : "memory");
+            else BLOCK_SYNC();
+        } else if (sync) __syncwarp();
         cur = nxt;
         nxt = nn;
         aux = auxn;
@@ -414,6 +420,36 @@ __device__ __forceinline__ void newton_rhs(Smem &s)
     BLOCK_SYNC();
 }
 
+#ifdef UCLGPU_PRODUCT_FORM
+// X = inv(L11), Y = inv(U11) on their closure patterns (uclchem_b200/product_form.py): level programs
+// from the factor storage into the staging buffer -- the flux array, dead outside rhs_eval.  GROUP = 0:
+// whole CTA, staging header written by the caller before a block barrier.  GROUP > 0: the GROUP threads
+// from tid_base on, on their own named barrier.
+template <int GROUP>
+__device__ __forceinline__ void pf_inverse_levels(Smem &s, uint32_t tid_base)
+{
+    static_assert(NET_PF_NSTG <= NREAC, "staging buffer is the flux array");
+    const double *val = s.val;
+    double *stg = s.flux;
+    if (GROUP) {
+        for (int i = (int)(threadIdx.x - tid_base); i < NET_N0; i += GROUP) stg[NET_PF_DIAG0 + i] = val[net_diag_pos[i]];
+        if (threadIdx.x == tid_base) stg[NET_PF_ONE] = 1.0;
+        asm volatile("barrier.sync 2, %0;" ::"n"(GROUP ? GROUP : 32) : "memory");
+        run_levels<4, GROUP>(
+            net_pf_side_desc, net_pf_side_terms, net_pf_side_units, NET_PF_SIDE_NUNITS,
+            [&](uint32_t t) { return make_double2(val[t >> 16], stg[t & 0xFFFFu]); },
+            [](uint32_t target) { return (uint32_t)__ldg(net_pf_inv_scale + target); },
+            [&](uint32_t target, double acc, uint32_t sc) { stg[target] = -stg[sc] * acc; }, tid_base);
+    } else {
+        run_levels<4>(
+            net_pf_inv_desc, net_pf_inv_terms, net_pf_inv_units, NET_PF_INV_NUNITS,
+            [&](uint32_t t) { return make_double2(val[t >> 16], stg[t & 0xFFFFu]); },
+            [](uint32_t target) { return (uint32_t)__ldg(net_pf_inv_scale + target); },
+            [&](uint32_t target, double acc, uint32_t sc) { stg[target] = -stg[sc] * acc; });
+    }
+}
+#endif
+
 // In-place inverse of the dense trailing block by Gauss-Jordan elimination without
 // pivoting.  Each thread keeps a GJ_B x GJ_B tile of the block in registers for all M steps;
 // per step only the pivot row, pivot column and 1/pivot go through shared memory (double
@@ -489,6 +525,15 @@ __device__ __noinline__ bool dense_inverse(Smem &s)
             }
         if (tid == 0) s.gj_piv[0] = ok ? 1.0 : 0.0; // every participant saw the same pivots
     }
+#if defined(UCLGPU_PRODUCT_FORM) && defined(UCLGPU_PF_OVERLAP)
+    else {
+        // The warps that have no tile (NT - GJ_NTHR threads) form the explicit inverses of the sparse
+        // factors meanwhile: the inverse program reads only L11 / U11 (final since the factor levels)
+        // and writes only the staging buffer, so it shares nothing with the Gauss-Jordan loop.
+        static_assert(NT - GJ_NTHR == NET_PF_SIDE_THREADS, "side group size is baked into the unit table");
+        pf_inverse_levels<NT - GJ_NTHR>(s, (uint32_t)GJ_NTHR);
+    }
+#endif
     BLOCK_SYNC();
     return s.gj_piv[0] != 0.0;
 }
@@ -517,16 +562,13 @@ __device__ __noinline__ bool factor_p(Smem &s, Blk &b)
         // X = inv(L11), Y = inv(U11) on their closure patterns: level programs into the staging buffer
         // (the flux array: dead outside rhs_eval), then one copy into the final positions -- entries that
         // exist in L11 / U11 are overwritten (not needed any more), fill entries go to the extra slots.
-        static_assert(NET_PF_NSTG <= NREAC, "staging buffer is the flux array");
         double *stg = s.flux;
+#ifndef UCLGPU_PF_OVERLAP
         if (tid < NET_N0) stg[NET_PF_DIAG0 + tid] = val[net_diag_pos[tid]];
         if (tid == 0) stg[NET_PF_ONE] = 1.0;
         BLOCK_SYNC();
-        run_levels<4>(
-            net_pf_inv_desc, net_pf_inv_terms, net_pf_inv_units, NET_PF_INV_NUNITS,
-            [&](uint32_t t) { return make_double2(val[t >> 16], stg[t & 0xFFFFu]); },
-            [](uint32_t target) { return (uint32_t)__ldg(net_pf_inv_scale + target); },
-            [&](uint32_t target, double acc, uint32_t sc) { stg[target] = -stg[sc] * acc; });
+        pf_inverse_levels<0>(s, 0u);
+#endif  // with UCLGPU_PF_OVERLAP the idle warps of dense_inverse have done this already
         for (int i = tid; i < NET_PF_NX + NET_PF_NY; i += NT) val[net_pf_final_pos[i]] = stg[i];
         BLOCK_SYNC();
     }

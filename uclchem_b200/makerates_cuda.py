@@ -506,6 +506,11 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     assert pf.nstg <= net.nreac, "the staging buffer of the inverse program is the flux array"
     _emit_program(w, "net_pf_inv", gen.pf_inv)
     w(_c_array("net_pf_inv_scale", gen.pf_inv_scale, "uint16_t"))
+    # the same program in passes of PF_SIDE_THREADS slots: run by the warps that idle during the dense
+    # Gauss-Jordan inverse (-DUCLGPU_PF_OVERLAP)
+    side = NTHREADS - (((-(-sym.m // 5)) ** 2 + 31) & ~31)
+    w(f"#define NET_PF_SIDE_THREADS {side}\n")
+    _emit_program(w, "net_pf_side", gen.pf_inv, nthreads=side)
     w(_c_array("net_pf_final_pos", pf.final_pos, "uint16_t"))
     _emit_program(w, "net_pf_p1", [gen.pf_p1])
     _emit_program(w, "net_pf_tail", [gen.pf_tail])
