@@ -46,3 +46,64 @@ def test_disk_mode_refuses_to_mix_with_memory_mode():
     with pytest.raises(RuntimeError, match="Offending keys"):
         model.pre_flight_checklist(True, False, False, None, {"outputfile": "a.dat"})
     model.pre_flight_checklist(False, False, False, None, {"outputfile": "a.dat"})   # disk mode: fine
+
+
+class _OracleBackedLibrary:
+    """Test double for uclchem_b200._capi.Library: same `run_grid` contract, computed by the oracle.
+    Lets the host-side logic of uclchem_b200.model (argument handling, disk mode, return tuples) run on
+    the CPU; the product path never sees it."""
+
+    def __init__(self, oracle, net):
+        from uclchem_b200._capi import STAT_FIELDS
+        self.orc, self.net = oracle, net
+        self.nspec, self.neq, self.nreac, self.species = net.nspec, net.neq, net.nreac, list(net.names)
+        self._nstat, self._iint = len(STAT_FIELDS), STAT_FIELDS.index("nintervals")
+
+    def run_grid(self, kind, params, y0=None, timepoints=0, want_physics=False, want_chem=False, want_rates=False,
+                 step_budget=0):
+        ncell = params.shape[1]
+        tp = max(timepoints, 1)
+        out = {"y_final": np.zeros((ncell, self.neq)), "phys_final": np.zeros((ncell, 8)),
+               "flag": np.zeros(ncell, np.int32), "stats": np.zeros((ncell, self._nstat), np.int64),
+               "dissipation_time": np.zeros(ncell)}
+        if want_physics:
+            out["physics"] = np.zeros((ncell, timepoints + 1, 8))
+        if want_chem:
+            out["abund"] = np.zeros((ncell, timepoints + 1, self.nspec))
+        for c in range(ncell):
+            r = self.orc.run_model(kind, np.ascontiguousarray(params[:, c]), y0=None if y0 is None else y0[c],
+                                   timepoints=tp if timepoints else 500)
+            out["y_final"][c], out["phys_final"][c], out["flag"][c] = r["y_final"], r["phys_final"], r["flag"]
+            out["stats"][c, self._iint] = r["stats"]["nintervals"]
+            n = len(r["physics"])
+            if want_physics:
+                out["physics"][c, :n] = r["physics"]
+            if want_chem:
+                out["abund"][c, :n] = r["abund"]
+        return out
+
+
+def test_model_disk_mode_host_logic(oracle, net, tmp_path, monkeypatch):
+    """The sequence of tests/test_gpu_parity.py::test_disk_mode_files with the oracle behind the library
+    interface: outputFile / abundSaveFile written after the run, abundLoadFile seeding the next one."""
+    from uclchem_b200 import model
+    monkeypatch.setattr(model, "get_library", lambda *a, **k: _OracleBackedLibrary(oracle, net))
+    pd_ = {"initialDens": 1e4, "initialTemp": 10.0, "finalTime": 1e3}
+    full, save = tmp_path / "full.dat", tmp_path / "final.dat"
+    res = model.cloud(param_dict={**pd_, "outputFile": str(full), "abundSaveFile": str(save)}, out_species=["CO"])
+    assert res[0] == 0 and len(res) == 2 and res[1] > 0
+    phys, chem, _, start, flag = model.cloud(param_dict=pd_, return_array=True)
+    names, data = datio.read_output_file(full)
+    assert flag == 0 and names[8:] == net.names and data.shape == (phys.shape[0], 8 + net.nspec)
+    assert np.allclose(data[:, 8:], chem[:, 0, :], rtol=1e-5, atol=0) and np.allclose(data[:, 0], phys[:, 0, 0], rtol=1e-3)
+    assert phys[-1, 0, 0] == pytest.approx(1e3)
+    final = datio.read_abundances(save, net.nspec)
+    assert np.allclose(final, start, rtol=1e-5, atol=0)
+    res2 = model.cloud(param_dict={**pd_, "finalTime": 1e2, "abundLoadFile": str(save), "outputFile": str(full)})
+    _, data2 = datio.read_output_file(full)
+    keep = np.array([n not in ("BULK", "SURFACE", "E-") for n in net.names])
+    assert res2 == [0] and np.allclose(data2[0, 8:][keep], final[keep], rtol=1e-4, atol=1e-29)
+    with pytest.raises(NotImplementedError):
+        model.cloud(param_dict={**pd_, "columnFile": "c.dat"})
+    with pytest.raises(RuntimeError, match="Offending keys"):
+        model.cloud(param_dict={**pd_, "outputFile": str(full)}, return_array=True)
