@@ -220,6 +220,8 @@ def main():
                                "every DVODE retry, 1e5-1e7 steps, up to 573 s for ONE cell on one SM) are left out, "
                                "see bench.py docstring / DESIGN.md section 6"),
                 "cells_per_gpu": ncell,
+                "full_grid_measured": "all 10000 cells, one device-resident pass on one B200: 573.2 s = 17.4 models/s "
+                                      "(round 1, profiles/r01b_bench_full_grid_stderr.log); `--full-grid` re-measures it",
                 "timing": "L2 flushed (256 MiB write) between timed steps",
                 "warmup_step": f"one pass over a {n_warm}-cell stride of the same grid (same kernel and launch shape)"}
 
