@@ -107,3 +107,23 @@ def test_model_disk_mode_host_logic(oracle, net, tmp_path, monkeypatch):
         model.cloud(param_dict={**pd_, "columnFile": "c.dat"})
     with pytest.raises(RuntimeError, match="Offending keys"):
         model.cloud(param_dict={**pd_, "outputFile": str(full)}, return_array=True)
+
+
+def test_grid_trajectories_host_logic(oracle, net, monkeypatch):
+    """`*_grid(return_array=True)`: the reference's in-memory layout [time, point, field], one point per cell."""
+    from uclchem_b200 import model
+    monkeypatch.setattr(model, "get_library", lambda *a, **k: _OracleBackedLibrary(oracle, net))
+    g = model.cloud_grid({"initialDens": [1e3, 1e4, 1e5], "finalTime": [1e2, 1e3, 1e2]}, out_species=["CO"],
+                         return_array=True, timepoints=40)
+    assert g["physics_array"].shape == (41, 3, 8) and g["chemical_abun_array"].shape == (41, 3, net.nspec)
+    assert (g["flag"] == 0).all() and g["out_species"].shape == (3, 1)
+    for c in range(3):
+        n = int(g["nrows"][c])
+        t = g["physics_array"][:n, c, 0]
+        assert t[0] == 0.0 and (np.diff(t) > 0).all() and t[-1] == pytest.approx([1e2, 1e3, 1e2][c])
+        assert (g["physics_array"][n:, c, 0] == 0.0).all()
+        assert np.allclose(g["chemical_abun_array"][n - 1, c], g["abundances"][c], rtol=1e-12)
+        assert g["physics_array"][0, c, 1] == pytest.approx([1e3, 1e4, 1e5][c])
+    assert g["nrows"][1] > g["nrows"][0]
+    with pytest.raises(RuntimeError, match="Offending keys"):
+        model.cloud_grid({"initialDens": [1e3, 1e4], "outputFile": "x.dat"})

@@ -147,9 +147,14 @@ def cshock(shock_vel, timestep_factor=0.01, minimum_temperature=0.0, param_dict=
 # ---------------------------------------------------------------------------------------
 # grids: what scripts/grid.py does with a process pool, in one call
 # ---------------------------------------------------------------------------------------
-def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None):
+def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None, return_array=False,
+              return_rates=False, timepoints=TIMEPOINTS):
     lib = get_library()
     pd_ = _lower(param_dict)
+    file_keys = [k for k in pd_ if k.endswith("file")]
+    if file_keys:   # one file name cannot hold a grid; the reference's grid scripts build one name per model
+        raise RuntimeError("file output is per model; use return_array=True for grids.\n"
+                           f"Offending keys: {', '.join(file_keys)}")
     pd_.update(extra)
     params = params_from_dict(pd_)
     ncell = params.shape[1]
@@ -160,9 +165,18 @@ def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None):
             sc = np.broadcast_to(sc, (ncell, sc.shape[0]))
         y0 = np.zeros((ncell, lib.neq))
         y0[:, : lib.nspec] = sc[:, : lib.nspec]
-    out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0)
+    out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if return_array else 0,
+                       want_physics=return_array, want_chem=return_array, want_rates=return_array and return_rates)
     res = {"flag": out["flag"], "abundances": out["y_final"][:, : lib.nspec], "physics": out["phys_final"],
            "stats": out["stats"], "species": lib.species}
+    if return_array:
+        # the reference's in-memory layout (wrap.f90:549-560): [time, point, field] with one "point" per cell;
+        # rows past a model's last output time stay zero, `nrows` says how many are filled per cell
+        res["physics_array"] = np.ascontiguousarray(np.swapaxes(out["physics"], 0, 1))
+        res["chemical_abun_array"] = np.ascontiguousarray(np.swapaxes(out["abund"], 0, 1))
+        if return_rates:
+            res["rates_array"] = np.ascontiguousarray(np.swapaxes(out["rates"], 0, 1))
+        res["nrows"] = np.minimum(out["stats"][:, 7] + 1, timepoints + 1)
     if out_species:
         res["out_species"] = out["y_final"][:, [lib.species.index(s) for s in out_species]]
     if kind == "cshock":
@@ -170,20 +184,27 @@ def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None):
     return res
 
 
-def cloud_grid(param_dict, starting_chemistry=None, out_species=None):
+def cloud_grid(param_dict, starting_chemistry=None, out_species=None, return_array=False, return_rates=False,
+               timepoints=TIMEPOINTS):
     """Integrate a grid of cloud models.  Array-valued entries of ``param_dict`` are per-cell
     columns, scalars broadcast.  Returns a dict with per-cell ``flag`` (constants.f90 codes),
-    final ``abundances`` [ncell, nspec], final ``physics`` [ncell, 8] and solver ``stats``."""
-    return _run_grid("cloud", param_dict, starting_chemistry, {}, out_species)
+    final ``abundances`` [ncell, nspec], final ``physics`` [ncell, 8] and solver ``stats``; with
+    ``return_array`` also the trajectories in the reference's in-memory layout
+    (``physics_array`` [timepoints+1, ncell, 8], ``chemical_abun_array`` [timepoints+1, ncell, nspec],
+    ``rates_array`` with ``return_rates``) and ``nrows``, the number of filled rows per cell."""
+    return _run_grid("cloud", param_dict, starting_chemistry, {}, out_species, return_array, return_rates, timepoints)
 
 
-def hot_core_grid(temp_indx, max_temperature, param_dict, starting_chemistry=None, out_species=None):
+def hot_core_grid(temp_indx, max_temperature, param_dict, starting_chemistry=None, out_species=None,
+                  return_array=False, return_rates=False, timepoints=TIMEPOINTS):
     return _run_grid("hot_core", param_dict, starting_chemistry,
-                     {"temp_indx": temp_indx, "max_temperature": max_temperature}, out_species)
+                     {"temp_indx": temp_indx, "max_temperature": max_temperature}, out_species, return_array,
+                     return_rates, timepoints)
 
 
 def cshock_grid(shock_vel, param_dict, timestep_factor=0.01, minimum_temperature=0.0, starting_chemistry=None,
-                out_species=None):
+                out_species=None, return_array=False, return_rates=False, timepoints=TIMEPOINTS):
     return _run_grid("cshock", param_dict, starting_chemistry,
                      {"shock_vel": shock_vel, "timestep_factor": timestep_factor,
-                      "minimum_temperature": minimum_temperature}, out_species)
+                      "minimum_temperature": minimum_temperature}, out_species, return_array, return_rates,
+                     timepoints)
