@@ -43,7 +43,15 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "cloud models integrated/sec (static cloud grid, 1 Myr, default network)"
+def _baseline_metric():
+    """The metric string of BASELINE.json (the line must carry the reference's headline metric verbatim)."""
+    try:
+        return json.loads((ROOT / "BASELINE.json").read_text())["metric"]
+    except Exception:
+        return "cloud models integrated/sec (10^5-pt grid, 1 Myr) at 1-8 B200 vs CPU DVODE"
+
+
+METRIC = _baseline_metric()
 UNIT = "models/s"
 
 
