@@ -238,7 +238,11 @@ extern "C" int uclgpu_work_model(double *out)
 {
     // {F_rhs, F_jac, F_lu, F_solve, F_rates (flop per call), bytes per interval, 0, 0}
     if (!out) return UCLGPU_ERR_BAD_ARGUMENT;
+#ifdef UCLGPU_PRODUCT_FORM   // algorithmic work of the product-form programs (product_form.py)
+    out[0] = NET_FLOP_RHS; out[1] = NET_FLOP_JAC; out[2] = NET_FLOP_LU_PF; out[3] = NET_FLOP_SOLVE_PF;
+#else
     out[0] = NET_FLOP_RHS; out[1] = NET_FLOP_JAC; out[2] = NET_FLOP_LU; out[3] = NET_FLOP_SOLVE;
+#endif
     out[4] = NET_FLOP_RATES; out[5] = NET_BYTES_INTERVAL; out[6] = out[7] = 0.0;
     return 0;
 }

@@ -502,6 +502,9 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     w("\n// ---- product-form solves (product_form.py; device side behind -DUCLGPU_PRODUCT_FORM) ----------\n")
     pf = gen.pf
     w(f"#define NET_NVAL_PF {pf.nval_pf}\n#define NET_PF_NX {pf.nx}\n#define NET_PF_NY {pf.ny}\n")
+    f_solve_pf = 2 * (pf.stats["p1_terms"] + st_["tail_terms"] + pf.stats["p4_terms"] + pf.stats["p5_terms"]) + 2 * sym.m ** 2
+    f_lu_pf = f_lu + 2 * pf.stats["inv_terms"]
+    w(f"#define NET_FLOP_SOLVE_PF {float(f_solve_pf)}\n#define NET_FLOP_LU_PF {float(f_lu_pf)}\n")
     w(f"#define NET_PF_DIAG0 {pf.stg_diag0}\n#define NET_PF_ONE {pf.stg_one}\n#define NET_PF_NSTG {pf.nstg}\n")
     assert pf.nstg <= net.nreac, "the staging buffer of the inverse program is the flux array"
     _emit_program(w, "net_pf_inv", gen.pf_inv)
