@@ -66,3 +66,29 @@ def test_no_cpu_fallback_without_device():
 def test_missing_library_fails_loudly():
     with pytest.raises(_capi.UclgpuError, match="no CPU fallback"):
         _capi.Library("no_such_network")
+
+
+def test_every_key_of_the_reference_parser_is_accounted_for():
+    """dictionaryParser (wrap.f90:699-983) accepts these keys (names read from the reference, lower case).
+    All of them are parameters of the GPU path or documented as not supported; anything else raises the
+    reference's PARAMETER_READ_ERROR semantics (KeyError here)."""
+    from uclchem_b200.params import _IGNORED
+    parser_keys = [
+        "alpha", "beta", "gamma", "initialtemp", "initialdens", "finaldens", "currenttime", "finaltime", "radfield",
+        "zeta", "freezefactor", "rout", "rin", "baseav", "points", "bm0", "endatfinaldensity", "freefall",
+        "freefallfactor", "desorb", "h2desorb", "crdesorb", "uvdesorb", "thermdesorb", "instantsublimation",
+        "cosmicrayattenuation", "ionmodel", "improvedh2crpdissociation", "ion", "fhe", "fc", "fo", "fn", "fs", "fmg",
+        "fsi", "fcl", "fp", "ff", "outspecies", "writestep", "ebmaxh2", "epsilon", "uvcreff", "ebmaxcr", "phi",
+        "ebmaxuvcr", "uv_yield", "metallicity", "omega", "reltol", "abstol_factor", "abstol_min", "jacobian",
+        "abundsavefile", "abundloadfile", "outputfile", "ratefile", "fluxfile", "columnfile", "fh", "ntime",
+        "trajecfile"]
+    # not offered by the GPU path: per-reaction alpha/beta/gamma overrides (rate tables are compiled into the
+    # library), the user-Jacobian switch (the Jacobian is always analytic) and the postprocess trajectory inputs
+    unsupported = {"alpha", "beta", "gamma", "jacobian", "ntime", "trajecfile"}
+    for k in parser_keys:
+        if k in unsupported:
+            with pytest.raises(KeyError):
+                params_from_dict({k: 1.0})
+        else:
+            assert k in PARAM_INDEX or k in _IGNORED, k
+            params_from_dict({k: 1 if k in ("ion", "points") else ("x.dat" if k.endswith("file") else 1.0)})
