@@ -38,6 +38,8 @@ def test_param_dict_semantics():
         params_from_dict({"initialDensity": 1e4})
     with pytest.raises(ValueError):
         params_from_dict({"initialDens": [1, 2, 3], "zeta": [1, 2]})
+    with pytest.raises(ValueError, match="multi-parcel"):   # refused, not silently treated as one point
+        params_from_dict({"points": 3})
     # single-precision default literals are kept
     assert default_params(1)[PARAM_INDEX["fhe"], 0] == float(np.float32(0.1))
 

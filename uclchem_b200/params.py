@@ -91,4 +91,9 @@ def params_from_dict(param_dict: dict | None, ncell: int | None = None) -> np.nd
             out[PARAM_INDEX[k], :] = [_to_float(k, x) for x in np.ravel(v)]
         else:
             out[PARAM_INDEX[k], :] = _to_float(k, v)
+    if (out[PARAM_INDEX["points"]] != 1.0).any():
+        # multi-parcel clouds couple their parcels through column densities (chemistry.f90:169-181):
+        # not a set of independent cells, and not built -- refuse rather than ignore
+        raise ValueError("points > 1 (multi-parcel clouds) is not supported by the GPU path: "
+                         "every cell of a grid is a single-point model")
     return out
