@@ -238,7 +238,7 @@ def main():
         if rank != 0:
             return
         cores = cpu_cores()
-        deadline = 120.0
+        deadline = max(30.0, min(120.0, 240.0 / max(1, a.steps)))   # the whole run stays within a few minutes
         for w in range(a.warmup):   # results discarded: a short bound is enough to page the library in
             log(f"reference arm: warm-up sample {w + 1}/{a.warmup} on {cores} cores")
             run_oracle_sample(params, cores, offset=1 + w, deadline_s=30.0)
