@@ -15,6 +15,20 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _built_libraries():
+    """The suite needs the in-tree libraries (`__graft_entry__.build()` makes them).  On a fresh
+    checkout with nvcc present they are compiled here once (cross-compilation needs no GPU); building
+    is not a fallback of any kind -- a missing library is still an error in the product path."""
+    import shutil
+    from uclchem_b200 import build
+    from uclchem_b200._capi import library_path
+    if not library_path("default").exists() and (shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists()):
+        build.compile("default")
+    from oracle import oracle as orc
+    orc.build()
+
+
 @pytest.fixture(scope="session")
 def net():
     from uclchem_b200.network import load_default

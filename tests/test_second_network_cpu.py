@@ -131,3 +131,18 @@ def _count(name, element):
         if sym == element:
             tot += int(num) if num else 1
     return tot
+
+
+def test_device_library_for_the_second_network_builds_and_loads(net2):
+    """`libuclgpu_crp_photo.so` (compact shared-memory layout, dense threshold 0.95: uclchem_b200/build.py)
+    compiles for sm_100a, loads without a GPU and reports this network; no compute call here."""
+    import shutil
+    from uclchem_b200 import build
+    from uclchem_b200._capi import EXPORTED, Library
+    if not (shutil.which("nvcc") or __import__("pathlib").Path("/usr/local/cuda/bin/nvcc").exists()):
+        pytest.skip("nvcc not available")
+    so = build.compile("crp_photo")
+    L = Library("crp_photo")
+    assert so.exists() and (L.nspec, L.nreac, L.naug) == (net2.nspec, net2.nreac, 338) and L.tag == "crp_photo"
+    assert all(hasattr(L.lib, sym) for sym in EXPORTED)
+    assert L.species == net2.names

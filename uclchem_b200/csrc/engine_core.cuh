@@ -91,6 +91,9 @@ struct Scalars {
 // factor_p also forms the explicit sparse inverses of the factors of the sparse pivots (in place +
 // NET_NVAL_PF - NET_NVAL fill slots) and lin_solve is five wide levels; the result is left in s.tmpv.
 // CPU-validated (tests/test_product_form_cpu.py); not the default until it has been run on a B200.
+#if defined(UCLGPU_PRODUCT_FORM) && defined(UCLGPU_COMPACT_SMEM)
+#error "UCLGPU_COMPACT_SMEM aliases the flux array, which is the staging buffer of UCLGPU_PRODUCT_FORM"
+#endif
 #ifdef UCLGPU_PRODUCT_FORM
 #define NET_NVAL_STORE NET_NVAL_PF
 #define SOLVE_RESULT(s) ((s).tmpv)
@@ -102,15 +105,34 @@ struct Scalars {
 struct __align__(16) Smem {
     double val[(NET_NVAL_STORE + 7) & ~7];
     double rate[(NREAC + 7) & ~7];
+#ifdef UCLGPU_COMPACT_SMEM
+    // Larger networks (crp_photo: 136 KB Newton matrix) do not leave room for everything.  The flux
+    // array is live only inside rhs_eval; the solve vectors and the Gauss-Jordan pivot buffers are
+    // live only between two RHS evaluations (newton_rhs -> lin_solve -> read-out, and dense_inverse),
+    // so they share its storage.  Not combinable with the product form (its staging buffer is flux).
+    union {
+        double flux[(NREAC + 7) & ~7];
+        struct {
+            double xs[NAUGP];
+            double tmpv[NAUGP];
+            double gj_row[2][GJ_PAD], gj_col[2][GJ_PAD], gj_piv[2];
+        };
+    };
+#else
     double flux[(NREAC + 7) & ~7];
+#endif
     double y[NEQP + 8];        // iterate + ext slots y[NEQ+0..3] = {1, blr, 1/safeMantle, tau}
     double yh[LMAXORD][NEQP];  // Nordsieck array
     double ewt[NEQP], savf[NEQP], acor[NEQP], atol[NEQP], abund[NEQP];
+#ifndef UCLGPU_COMPACT_SMEM
     double xs[NAUGP];          // linear-solve vector, elimination (new) ordering
     double tmpv[NAUGP];
+#endif
     double invd[NAUGP];        // reciprocal sparse pivots (copied out of val after each factorisation)
     double red[2][32];
+#ifndef UCLGPU_COMPACT_SMEM
     double gj_row[2][GJ_PAD], gj_col[2][GJ_PAD], gj_piv[2];
+#endif
     Scalars st;
 };
 

@@ -506,7 +506,7 @@ def emit(gen: Generated, outdir: Path, tag: str) -> Path:
     f_lu_pf = f_lu + 2 * pf.stats["inv_terms"]
     w(f"#define NET_FLOP_SOLVE_PF {float(f_solve_pf)}\n#define NET_FLOP_LU_PF {float(f_lu_pf)}\n")
     w(f"#define NET_PF_DIAG0 {pf.stg_diag0}\n#define NET_PF_ONE {pf.stg_one}\n#define NET_PF_NSTG {pf.nstg}\n")
-    assert pf.nstg <= net.nreac, "the staging buffer of the inverse program is the flux array"
+    # (the product-form build static_asserts NET_PF_NSTG <= NREAC: its staging buffer is the flux array)
     _emit_program(w, "net_pf_inv", gen.pf_inv)
     w(_c_array("net_pf_inv_scale", gen.pf_inv_scale, "uint16_t"))
     # the same program in passes of PF_SIDE_THREADS slots: run by the warps that idle during the dense
