@@ -249,9 +249,13 @@ static int integrate_ode_system(orc_model *m)
     m->stats.nst += v->nst; m->stats.nfe += v->nfe; m->stats.nje += v->nje; m->stats.nlu += v->nlu;
     m->stats.nni += v->nni; m->stats.ncfn += v->ncfn; m->stats.netf += v->netf;
     if (orc_deadline_expired()) return ORC_FLAG_DEADLINE; /* benchmark guard, not reference behaviour */
-    if (istate != 2 && getenv("ORC_DEBUG"))
-        fprintf(stderr, "[oracle] ISTATE %d at t=%.6e yr (target %.6e yr) T=%.3f nst=%ld\n", istate,
-                m->current_time / SECONDS_PER_YEAR, m->target_time / SECONDS_PER_YEAR, m->gastemp, v->nst);
+    {
+        const char *dbg = getenv("ORC_DEBUG"); /* "1": failed DVODE calls, "2": every call */
+        if (dbg && (istate != 2 || dbg[0] == '2'))
+            fprintf(stderr, "[oracle] ISTATE %d at t=%.6e yr (target %.6e yr) T=%.3f nst=%ld netf=%ld ncfn=%ld nje=%ld nlu=%ld\n",
+                    istate, m->current_time / SECONDS_PER_YEAR, m->target_time / SECONDS_PER_YEAR, m->gastemp, v->nst,
+                    v->netf, v->ncfn, v->nje, v->nlu);
+    }
     switch (istate) {
     case -1:
     case -4:

@@ -43,16 +43,12 @@ def generate(tag: str = "default", network_f90: str | None = None) -> Path:
     return emit(Generated(net, dense_threshold=thr), CSRC / "generated" / tag, tag)
 
 
-# build variants: suffix of the library name -> extra nvcc defines
+# build variants: suffix of the library name -> extra nvcc defines.  The default build uses the product-form
+# solves with the inverse program overlapped with the dense Gauss-Jordan inverse (engine_core.cuh); "sub" keeps
+# the level-scheduled substitution for A/B runs (`python tools/gpu_ab.py default_sub default 592`).
 VARIANTS = {
     "": [],
-    # product-form triangular solves (product_form.py): CPU-validated, to be A/B-tested on a B200
-    # (`python tools/gpu_ab.py default default_pf 592`) before it becomes the default
-    "pf": ["-DUCLGPU_PRODUCT_FORM"],
-    # ... with the inverse program on the warps that idle during the dense Gauss-Jordan inverse
-    "pfo": ["-DUCLGPU_PRODUCT_FORM", "-DUCLGPU_PF_OVERLAP"],
-    # DVSET with el[] / tau[] in registers (engine_bdf.cuh): same statements, not yet run on a B200
-    "vs": ["-DUCLGPU_VSET_REG"],
+    "sub": ["-DUCLGPU_NO_PRODUCT_FORM"],
 }
 
 
@@ -63,7 +59,7 @@ def compile(tag: str = "default", force: bool = False, verbose: bool = False, va
         generate(tag)
     LIBDIR.mkdir(exist_ok=True)
     out = LIBDIR / (f"libuclgpu_{tag}_{variant}.so" if variant else f"libuclgpu_{tag}.so")
-    srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_bdf.cuh",
+    srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_gj.cuh", CSRC / "engine_bdf.cuh",
             CSRC / "engine_model.cuh", gen, _PKG.parent / "include" / "uclgpu.h"]
     if not force and out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return out

@@ -45,12 +45,10 @@
 #define T0_BEGIN BLOCK_SYNC(); if (threadIdx.x == 0) {
 #define T0_END } BLOCK_SYNC();
 
-#ifdef UCLGPU_VSET_REG
-// DVSET dvode.f90:7616 (BDF branch :7739-7786); thread 0 only. 1-based arrays.  Build variant
-// (-DUCLGPU_VSET_REG, not yet run on a B200): this runs on one thread while the rest of the CTA waits,
-// so the EL recurrences are unrolled over the maximum order with predicates and el[] / tau[] stay in
-// registers (statement order and arithmetic are DVSET's) instead of round-tripping through shared
-// memory for every update.
+// DVSET dvode.f90:7616 (BDF branch :7739-7786); thread 0 only. 1-based arrays.  This runs on one thread
+// while the rest of the CTA waits, so the EL recurrences are unrolled over the maximum order with
+// predicates and el[] / tau[] stay in registers (statement order and arithmetic are DVSET's; bitwise the
+// loop form, tests/test_vset_variant_cpu.py) instead of round-tripping through shared memory.
 __device__ __noinline__ void vset_dev(Scalars &st)
 {
     const int nq = st.nq, l = st.l;
@@ -121,59 +119,6 @@ __device__ __noinline__ void vset_dev(Scalars &st)
     for (int i = 1; i <= LMAXORD; i++)
         if (i <= l) st.el[i] = el[i];
 }
-#else
-// DVSET dvode.f90:7616 (BDF branch :7739-7786); thread 0 only. 1-based arrays.
-__device__ __noinline__ void vset_dev(Scalars &st)
-{
-    double *el = st.el, *tq = st.tq, *tau = st.tau;
-    const int nq = st.nq, l = st.l;
-    const double flotl = (double)l;
-    const int nqm1 = nq - 1, nqm2 = nq - 2;
-    for (int i = 3; i <= l; i++) el[i] = 0.0;
-    el[1] = 1.0;
-    el[2] = 1.0;
-    double alph0 = -1.0, ahatn0 = -1.0, hsum = st.h, rxi = 1.0, rxis = 1.0;
-    if (nq != 1) {
-        for (int j = 1; j <= nqm2; j++) {
-            hsum += tau[j];
-            rxi = st.h / hsum;
-            int jp1 = j + 1;
-            alph0 -= 1.0 / (double)jp1;
-            for (int iback = 1; iback <= jp1; iback++) {
-                int i = (j + 3) - iback;
-                el[i] = el[i] + el[i - 1] * rxi;
-            }
-        }
-        alph0 -= 1.0 / (double)nq;
-        rxis = -el[2] - alph0;
-        hsum += tau[nqm1];
-        rxi = st.h / hsum;
-        ahatn0 = -el[2] - rxi;
-        for (int iback = 1; iback <= nq; iback++) {
-            int i = (nq + 2) - iback;
-            el[i] = el[i] + el[i - 1] * rxis;
-        }
-    }
-    double t1 = 1.0 - ahatn0 + alph0;
-    double t2 = 1.0 + (double)nq * t1;
-    tq[2] = fabs(alph0 * t2 / t1);
-    tq[5] = fabs(t2 / (el[l] * rxi / rxis));
-    if (st.nqwait == 1) {
-        double cnqm1 = rxis / el[l];
-        double t3 = alph0 + 1.0 / (double)nq;
-        double t4 = ahatn0 + rxi;
-        double elp = t3 / (1.0 - t4 + t3);
-        tq[1] = fabs(elp / cnqm1);
-        hsum += tau[nq];
-        rxi = st.h / hsum;
-        double t5 = alph0 - 1.0 / (double)(nq + 1);
-        double t6 = ahatn0 - rxi;
-        elp = t2 / (1.0 - t6 + t5);
-        tq[3] = fabs(elp * rxi * (flotl + 1.0) * t5);
-    }
-    tq[4] = V_CORTES * tq[2];
-}
-#endif // UCLGPU_VSET_REG
 
 // DVJUST dvode.f90:7790 (BDF :7862-7921).  Ends with a barrier.
 __device__ __noinline__ void vjust_dev(Smem &s, int iord)

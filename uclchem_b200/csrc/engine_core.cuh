@@ -36,7 +36,15 @@
 #define NAUGP ((NAUG + 7) & ~7)
 #define GJ_B 5                              /* square register tile of the dense Gauss-Jordan inverse */
 #define GJ_NT ((MDENSE + GJ_B - 1) / GJ_B)  /* tiles per side */
-#define GJ_PAD (GJ_NT * GJ_B + 4)
+#define GJ_TS (GJ_B * GJ_B)                 /* doubles per tile; panels are arrays of tiles (odd pitch: conflict-free) */
+// shared-memory panels of the blocked Gauss-Jordan inverse (dense_inverse, engine_la.cuh), offsets in doubles
+#define GJ_CP 0                             /* column panel, 2 x GJ_NT tiles [k][r] (double buffered) */
+#define GJ_RO (2 * GJ_NT * GJ_TS)           /* row panel before scaling, GJ_NT tiles [k][c] */
+#define GJ_RN (3 * GJ_NT * GJ_TS)           /* row panel times the inverse of the diagonal tile */
+#define GJ_DI (4 * GJ_NT * GJ_TS)           /* inverse of the diagonal tile, 2 x 26 (double buffered) */
+#define GJ_MI (GJ_DI + 52)                  /* minus the identity tile */
+#define GJ_OK (GJ_MI + 26)                  /* "all pivots finite" flag */
+#define GJ_PANEL (GJ_OK + 2)
 
 // ---- constants.f90:2-18, surfacereactions.f90:34-52 (single-precision literals kept)
 #define C_KBOLTZ 1.38065040e-16
@@ -87,12 +95,16 @@ struct Scalars {
     double dbg[64];
 };
 
-// Product-form solves (uclchem_b200/product_form.py): with -DUCLGPU_PRODUCT_FORM
-// factor_p also forms the explicit sparse inverses of the factors of the sparse pivots (in place +
-// NET_NVAL_PF - NET_NVAL fill slots) and lin_solve is five wide levels; the result is left in s.tmpv.
-// CPU-validated (tests/test_product_form_cpu.py); not the default until it has been run on a B200.
-#if defined(UCLGPU_PRODUCT_FORM) && defined(UCLGPU_COMPACT_SMEM)
-#error "UCLGPU_COMPACT_SMEM aliases the flux array, which is the staging buffer of UCLGPU_PRODUCT_FORM"
+// Product-form solves (uclchem_b200/product_form.py): factor_p also forms the explicit
+// sparse inverses of the factors of the sparse pivots (in place + NET_NVAL_PF - NET_NVAL fill slots) on the
+// warps that have no tile in the dense Gauss-Jordan inverse, and lin_solve is five wide levels; the result is
+// left in s.tmpv.  Default since round 2 (B200: solve 27.5 k -> 12.0 k cycles, 134.6 k -> 114.9 k cycles per
+// BDF step, <= 8e-4 dex against the substitution build on 584 config-2 cells).  Networks that need the compact
+// shared-memory layout (their flux array is aliased, and it is the staging buffer of the inverse program)
+// and builds with -DUCLGPU_NO_PRODUCT_FORM keep the level-scheduled substitution.
+#if !defined(UCLGPU_COMPACT_SMEM) && !defined(UCLGPU_NO_PRODUCT_FORM)
+#define UCLGPU_PRODUCT_FORM
+#define UCLGPU_PF_OVERLAP
 #endif
 #ifdef UCLGPU_PRODUCT_FORM
 #define NET_NVAL_STORE NET_NVAL_PF
@@ -107,15 +119,15 @@ struct __align__(16) Smem {
     double rate[(NREAC + 7) & ~7];
 #ifdef UCLGPU_COMPACT_SMEM
     // Larger networks (crp_photo: 136 KB Newton matrix) do not leave room for everything.  The flux
-    // array is live only inside rhs_eval; the solve vectors and the Gauss-Jordan pivot buffers are
-    // live only between two RHS evaluations (newton_rhs -> lin_solve -> read-out, and dense_inverse),
-    // so they share its storage.  Not combinable with the product form (its staging buffer is flux).
+    // array is live only inside rhs_eval; the solve vectors and the Gauss-Jordan panels are live only
+    // between two RHS evaluations (newton_rhs -> lin_solve -> read-out, and dense_inverse), so they
+    // share its storage.  Not combinable with the product form (its staging buffer is flux).
     union {
         double flux[(NREAC + 7) & ~7];
         struct {
             double xs[NAUGP];
             double tmpv[NAUGP];
-            double gj_row[2][GJ_PAD], gj_col[2][GJ_PAD], gj_piv[2];
+            double gj_pan[GJ_PANEL];
         };
     };
 #else
@@ -125,14 +137,22 @@ struct __align__(16) Smem {
     double yh[LMAXORD][NEQP];  // Nordsieck array
     double ewt[NEQP], savf[NEQP], acor[NEQP], atol[NEQP], abund[NEQP];
 #ifndef UCLGPU_COMPACT_SMEM
-    double xs[NAUGP];          // linear-solve vector, elimination (new) ordering
-    double tmpv[NAUGP];
-#endif
+    // xs / tmpv: linear-solve vectors (elimination ordering); invd: reciprocal sparse pivots (copied out of
+    // val at the end of factor_p).  None of the three is live while the dense block is inverted -- the
+    // Newton right-hand side is formed after the factorisation -- so the Gauss-Jordan panels (15.8 KB)
+    // alias them.
+    union {
+        struct {
+            double xs[NAUGP];
+            double tmpv[NAUGP];
+            double invd[NAUGP];
+        };
+        double gj_pan[GJ_PANEL];
+    };
+#else
     double invd[NAUGP];        // reciprocal sparse pivots (copied out of val after each factorisation)
-    double red[2][32];
-#ifndef UCLGPU_COMPACT_SMEM
-    double gj_row[2][GJ_PAD], gj_col[2][GJ_PAD], gj_piv[2];
 #endif
+    double red[2][32];
     Scalars st;
 };
 

@@ -6,6 +6,7 @@
 //   DVSOL/DGESL (dvode.f90:8698,12091)                -> lin_solve()
 #pragma once
 #include "engine_core.cuh"
+#include "engine_gj.cuh"
 
 // ---- team-program executor ---------------------------------------------------------
 // desc[slot] = {term_begin, target | nterms<<16 | log2(team)<<28}; teams are aligned
@@ -450,80 +451,29 @@ __device__ __forceinline__ void pf_inverse_levels(Smem &s, uint32_t tid_base)
 }
 #endif
 
-// In-place inverse of the dense trailing block by Gauss-Jordan elimination without
-// pivoting.  Each thread keeps a GJ_B x GJ_B tile of the block in registers for all M steps;
-// per step only the pivot row, pivot column and 1/pivot go through shared memory (double
-// buffered, one named barrier per step).  The step loop runs over diagonal tiles with the
-// GJ_B steps inside a tile unrolled, so "do I own the pivot row / column" is a comparison of
-// tile coordinates and every register index is static.  Every tile does the uniform update
-// a_ij -= col_i * (row_j * p); the tiles on the pivot's tile row / column then overwrite their
-// pivot row (a_kj p) / column (-a_ik p, p on the diagonal).
+// In-place inverse of the dense trailing block: blocked Gauss-Jordan elimination without pivoting
+// (engine_gj.cuh), one GJ_B x GJ_B register tile per thread, two named barriers per block step.
+// Returns false if a pivot is zero / not finite.  Ends with a block barrier.
 __device__ __noinline__ bool dense_inverse(Smem &s)
 {
     static_assert(GJ_NT * GJ_NT <= NT, "dense tile grid must fit the block");
     const int tid = threadIdx.x;
     double *T = s.val + NET_OFF_DENSE;
-    const int tr = tid / GJ_NT, tc = tid - tr * GJ_NT;
-    const bool active = tid < GJ_NT * GJ_NT;
-    const int i0 = tr * GJ_B, j0 = tc * GJ_B;
-    double a[GJ_B][GJ_B];
-#pragma unroll
-    for (int r = 0; r < GJ_B; r++)
-#pragma unroll
-        for (int c = 0; c < GJ_B; c++) {
-            int i = i0 + r, j = j0 + c;
-            a[r][c] = (active && i < MDENSE && j < MDENSE) ? T[i * MDENSE + j] : 0.0;
-        }
-    bool ok = true;
+    double *pan = s.gj_pan;
     constexpr int GJ_NTHR = (GJ_NT * GJ_NT + 31) & ~31; // whole warps take part in the named barrier
     if (tid < GJ_NTHR) {
+        GjTile t;
+        gj_load(t, T, tid);
+        gj_init_panel(pan, tid);
+        gj_publish(t, pan, tid, 0);
         for (int kb = 0; kb < GJ_NT; kb++) {
-            const bool own_r = active && tr == kb, own_c = active && tc == kb;
-#pragma unroll
-            for (int kk = 0; kk < GJ_B; kk++) {
-                const int k = kb * GJ_B + kk;
-                if (k >= MDENSE) break; // block-uniform
-                const int buf = k & 1;
-                if (own_r) {
-#pragma unroll
-                    for (int c = 0; c < GJ_B; c++) s.gj_row[buf][j0 + c] = a[kk][c];
-                }
-                if (own_c) {
-#pragma unroll
-                    for (int r = 0; r < GJ_B; r++) s.gj_col[buf][i0 + r] = a[r][kk];
-                    if (own_r) s.gj_piv[buf] = 1.0 / a[kk][kk];
-                }
-                asm volatile("barrier.sync 1, %0;" ::"r"(GJ_NTHR) : "memory");
-                const double p = s.gj_piv[buf];
-                if (!isfinite(p) || p == 0.0) ok = false;
-                double rp[GJ_B], cl[GJ_B];
-#pragma unroll
-                for (int c = 0; c < GJ_B; c++) rp[c] = s.gj_row[buf][j0 + c] * p;
-#pragma unroll
-                for (int r = 0; r < GJ_B; r++) cl[r] = s.gj_col[buf][i0 + r];
-#pragma unroll
-                for (int r = 0; r < GJ_B; r++)
-#pragma unroll
-                    for (int c = 0; c < GJ_B; c++) a[r][c] -= cl[r] * rp[c];
-                if (own_r) {
-#pragma unroll
-                    for (int c = 0; c < GJ_B; c++) a[kk][c] = rp[c];
-                }
-                if (own_c) {
-#pragma unroll
-                    for (int r = 0; r < GJ_B; r++) a[r][kk] = -cl[r] * p;
-                    if (own_r) a[kk][kk] = p;
-                }
-            }
+            asm volatile("barrier.sync 1, %0;" ::"n"(GJ_NTHR) : "memory");
+            gj_scale_row_panel(pan, tid, GJ_NTHR, kb);
+            asm volatile("barrier.sync 1, %0;" ::"n"(GJ_NTHR) : "memory");
+            gj_update(t, pan, tid, kb);
+            gj_publish(t, pan, tid, kb + 1);
         }
-#pragma unroll
-        for (int r = 0; r < GJ_B; r++)
-#pragma unroll
-            for (int c = 0; c < GJ_B; c++) {
-                int i = i0 + r, j = j0 + c;
-                if (active && i < MDENSE && j < MDENSE) T[i * MDENSE + j] = a[r][c];
-            }
-        if (tid == 0) s.gj_piv[0] = ok ? 1.0 : 0.0; // every participant saw the same pivots
+        gj_store(t, T, tid);
     }
 #if defined(UCLGPU_PRODUCT_FORM) && defined(UCLGPU_PF_OVERLAP)
     else {
@@ -535,7 +485,11 @@ __device__ __noinline__ bool dense_inverse(Smem &s)
     }
 #endif
     BLOCK_SYNC();
-    return s.gj_piv[0] != 0.0;
+    const bool ok = pan[GJ_OK] != 0.0;
+#if !defined(UCLGPU_PRODUCT_FORM) && !defined(UCLGPU_COMPACT_SMEM)
+    BLOCK_SYNC(); // the panels alias invd, which factor_p writes next: everyone must have read the flag
+#endif
+    return ok;
 }
 
 // Numeric factorisation of P (in s.val) on the generated pattern.  Sparse pivots end up stored
