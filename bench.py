@@ -1,30 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- cloud models integrated per second on B200 (BASELINE.json metric).
 
-A *step* is one pass of the hot path over one batch: the BASELINE config-2 workload, the
-10^4-point static-cloud grid (25 densities x 20 temperatures x 20 cosmic-ray rates, 1 Myr
-each, default network).  161 of its cells (1.6 %) are cells on which the reference algorithm
-itself does not terminate in bounded work: DVODE hits MXSTEP in every retry, and because
-`usepostprocess` is always .true. UCLCHEM's own stall guard (chemistry.f90:224-237) never
-fires, so the model crawls on for 1e5..1e7 steps (measured here: the slowest single cell needs
-~8e6 BDF steps = 573 s on one SM, hours on a CPU core, while the other 9 839 cells together need
-~40 s on 148 SMs).  A cell is one sequential chain of steps, so those few cells would set the
-pass time of ANY implementation and make the default run take tens of minutes.  Both arms
-therefore time the same bounded workload: the grid minus those 161 cells (indices committed in
-tools/config2_heavy_cells.npy).  `--full-grid` times all 10^4 cells (DESIGN.md section 6 has
-that measurement).  Per rank the work is fixed (weak scaling): with N ranks the job integrates
-N x 9 839 independent models and rank 0 gathers the results.
+Workload (N = 1): BASELINE config[1], the 10^4-point static-cloud grid (25 densities x 20 temperatures x 20
+cosmic-ray rates, 1 Myr each, default network), ALL of its cells.  With N ranks the zeta axis is refined N-fold
+(25 x 20 x 20N points, rank r owns every N-th zeta plane), so per-GPU work is fixed (weak scaling), the job
+integrates N x 10^4 distinct models, and rank 0 gathers every model's final abundances and flag.
 
-  value  : device-resident leg (parameters already in HBM, results left in HBM)
-  e2e    : the call a user makes -- uclgpu_run_grid through the C ABI with pinned HOST
-           buffers, H2D and D2H inside the timed region
-  roofline / fp64 : algorithmic work from the solver counters x the per-operation counts
-           the MakeRates CUDA back-end emits, over the CUDA-event time of the kernel
-  cpu_baseline : the oracle (CPU restatement of the reference algorithm: dense FD
-           Jacobian DVODE, cold restart per interval) on the box's host cores
+A *step* is one call of the hot path over one batch: an interleaved quarter of the rank's grid (cells whose flat
+index is congruent to step mod 4: every density and temperature, every fourth zeta), 2 500 models per GPU; four
+consecutive steps cover the grid once.  (A whole pass is ~35 s, and the driver's `--steps 20 --warmup 5` has to
+finish in minutes; a quarter keeps ~17 cells per SM in the work queue.)
 
-`--impl reference` times that CPU restatement alone (the reference Fortran cannot be
-compiled in this image: no Fortran compiler).
+The reference algorithm does not terminate in bounded work on ~1 % of these cells: the three-phase surface/bulk
+transfer has a kink at zero net surface growth, DVODE hits MXSTEP in every retry there, and UCLCHEM's own stall
+guard (chemistry.f90:224-237) is disabled by its always-on `usepostprocess`.  Both arms run
+every cell; `--step-budget` (default 100 000 BDF steps = 10 x MXSTEP, the most one output interval may take in
+the reference) bounds a single cell like the reference's guard was meant to, and cells that exhaust it are
+returned with INT_TOO_MANY_FAILS_ERROR and are NOT counted as integrated models -- their time is.
+
+  value  : models integrated / CUDA-event time of k_integrate in the same calls (inputs resident in HBM)
+  e2e    : models integrated / wall time of the calls a user makes -- uclgpu_run_grid through the C ABI with
+           pinned HOST buffers (H2D, kernel, D2H inside) plus, for N > 1, the gather to rank 0
+  roofline : algorithmic fp64 work (solver counters x per-operation counts from the MakeRates CUDA back-end,
+           LU of the dense block at 2/3 m^3) over kernel time, against a DFMA peak measured in this process;
+           `hbm` gives the algorithmic bytes against the measured copy bandwidth for completeness
+  cpu_baseline : the oracle (CPU restatement of the reference algorithm: dense finite-difference Jacobian DVODE,
+           cold restart per interval), work queue over all host cores, bounded sample
+
+`--impl reference` times that CPU restatement alone (the reference Fortran cannot be compiled in this image: no
+Fortran compiler).
 """
 from __future__ import annotations
 
@@ -43,6 +47,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+
 def _baseline_metric():
     """The metric string of BASELINE.json (the line must carry the reference's headline metric verbatim)."""
     try:
@@ -53,19 +58,27 @@ def _baseline_metric():
 
 METRIC = _baseline_metric()
 UNIT = "models/s"
+NSLICE = 4            # a step is one interleaved quarter of the rank's grid
+STEP_BUDGET = 100000  # BDF steps per cell: 10 x MXSTEP
 
 
-def config2_params(ncell_side=(25, 20, 20)):
-    """regular grid, no RNG."""
+def config2_params(ncell_side=(25, 20, 20), rank=0, world=1):
+    """regular grid, no RNG.  With `world` ranks the zeta axis has 20*world points
+    and rank r takes every world-th one (world = 1: the config-2 grid itself)."""
     from uclchem_b200.params import params_from_dict
     nd, nt, nz = ncell_side
     dens = 10 ** np.linspace(3, 7, nd)
     temp = np.linspace(10, 100, nt)
-    zeta = 10 ** np.linspace(0, 3, nz)
+    zeta = (10 ** np.linspace(0, 3, nz * world))[rank::world]
     D, T, Z = np.meshgrid(dens, temp, zeta, indexing="ij")
     return params_from_dict({"initialDens": D.ravel(), "initialTemp": T.ravel(), "zeta": Z.ravel(), "radfield": 1.0,
                              "baseAv": 2.0, "rout": 0.05, "finalTime": 1.0e6, "freefall": False,
                              "endAtFinalDensity": False})
+
+
+def slice_cells(ncell, q, nslice=NSLICE):
+    """Cells of step slice q: flat index congruent to q (mod nslice)."""
+    return np.arange(q % nslice, ncell, nslice)
 
 
 class ClockSampler:
@@ -125,146 +138,158 @@ def log(msg):
     print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
-def bounded_cells(ncell):
-    """Indices of the config-2 cells with bounded work (see the module docstring)."""
-    ok = np.ones(ncell, bool)
-    f = ROOT / "tools" / "config2_heavy_cells.npy"
-    if ncell == 10000:
-        ok[np.load(f)] = False
-    return np.where(ok)[0]
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_sample_order(ncell):
+    """Deterministic shuffle of the workload's cells: the CPU work queue takes them in this order, so that cheap
+    and expensive regions of the grid are mixed and a time-bounded prefix is a fair sample."""
+    return np.random.default_rng(20261017).permutation(ncell)
 
 
-def sample_cells(ncell, n, offset=0):
-    """`n` evenly spaced cells of the workload (deterministic; `offset` shifts the comb)."""
-    return (np.linspace(0, ncell - 1, n).astype(int) + offset) % ncell
-
-
-def run_oracle_sample(params, cores, offset=0, deadline_s=90.0):
-    """Time the CPU restatement on `cores` evenly spaced cells of the workload, one per core, with a
-    wall-clock bound: a model still running after `deadline_s` is stopped (oracle guard, flag -98) and
-    does not count.  Returns (models/s over the cells that finished, seconds, cell indices, y, flag)."""
+def run_oracle_sample(params, cores, seconds, cells=None):
+    """Time the CPU restatement on the workload: one work queue over `cores` threads (every core stays busy until
+    the bound), cells in `cpu_sample_order`, stopped `seconds` after the start.  A model still running at the
+    bound stops (oracle guard, flag -98) and is left out of numerator and denominator -- which favours the CPU
+    figure, because the cells that get cut are the slow ones.  Returns a dict."""
     from oracle.oracle import Oracle
     from uclchem_b200.network import load_default
-    idx = sample_cells(params.shape[1], cores, offset)
-    orc = Oracle(load_default())
-    orc.set_deadline(deadline_s)
+    order = cpu_sample_order(params.shape[1]) if cells is None else np.asarray(cells)
+    order = order[: max(cores, int(cores * seconds / 1.5))]   # more than the queue can finish (>= 1.5 s per model)
+    orc = Oracle(load_default(), native=True)
+    orc.set_deadline(seconds)
     t0 = time.perf_counter()
-    y, _, flag, _ = orc.run_grid(0, np.ascontiguousarray(params[:, idx]), nthreads=cores)
-    dt = time.perf_counter() - t0
+    y, _, flag, st, secs = orc.run_grid(0, np.ascontiguousarray(params[:, order]), nthreads=cores, timed=True)
+    wall = time.perf_counter() - t0
     orc.set_deadline(0.0)
-    done = int((flag != Oracle.FLAG_DEADLINE).sum())
-    return done / dt, dt, idx, y, flag
+    fin = (flag != Oracle.FLAG_DEADLINE) & (secs >= 0)
+    cut = (flag == Oracle.FLAG_DEADLINE) & (secs >= 0)
+    core_s = float(secs[fin].sum())
+    n_fin = int(fin.sum())
+    rate = cores * n_fin / core_s if core_s > 0 else 0.0
+    nst = st[:, 0].astype(np.float64)
+    return {"rate": rate, "wall": wall, "cells": order, "y": y, "flag": flag, "finished": fin, "n_finished": n_fin,
+            "n_cut": int(cut.sum()), "core_seconds": core_s,
+            "ms_per_bdf_step": 1e3 * core_s / nst[fin].sum() if n_fin else None,
+            "steps_per_model": float(nst[fin].mean()) if n_fin else None,
+            "seconds_per_model": core_s / n_fin if n_fin else None, "cflags": orc.cflags}
 
 
-def sample_text(idx, flag, dt, deadline_s):
-    cut = int((flag == -98).sum())
-    txt = f"{len(idx)} evenly spaced cells of the workload, one per host core, {dt:.1f} s"
-    if cut:
-        txt += (f"; {cut} of them were still running at the {deadline_s:.0f} s bound and are not counted "
-                "(the figure is then an upper bound of the CPU rate)")
-    return txt
+def cpu_baseline_dict(r, cores, seconds):
+    sample = (f"work queue over {cores} threads on a fixed shuffle of the workload's cells, stopped after {seconds:.0f} s: "
+              f"{r['n_finished']} models finished in {r['core_seconds']:.0f} core-seconds; {r['n_cut']} still running at "
+              "the bound are left out of numerator and denominator (they are the slow ones: this favours the CPU figure); "
+              "value = cores x finished / core-seconds of the finished models")
+    return {"value": r["rate"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+            "what": "CPU restatement of the reference algorithm (oracle/: DVODE MF=22, dense finite-difference Jacobian, "
+                    "LINPACK LU, cold restart per interval); the reference Fortran cannot be built in this image",
+            "ms_per_bdf_step_per_core": r["ms_per_bdf_step"], "bdf_steps_per_model": r["steps_per_model"],
+            "seconds_per_model_per_core": r["seconds_per_model"], "compile_flags": r["cflags"]}
 
 
-def assemble_line(*, a, world, ncell, workload, dt, kernel_ms, dt_e2e, launches, launches_e2e, stats, flags,
-                  clocks, work_model, fp64_peak_tflops, h2d_bytes, d2h_bytes, cpu, parity, traffic, stat_fields):
-    """The bench JSON line from measured quantities (pure function: unit-tested on the CPU)."""
-    f_rhs, f_jac, f_lu, f_solve, f_rates, b_interval = list(work_model)[:6]
+# ------------------------------------------------------------------------------------------------ JSON line
+def assemble_line(*, a, world, n_ok, n_cells, n_budget, workload, wall_s, kernel_ms, launches, stats, clocks,
+                  work_model, fp64_peak_tflops, h2d_bytes, d2h_bytes, cpu, parity, traffic, stat_fields,
+                  per_rank_kernel_ms=None, gather_bytes=0):
+    """The bench JSON line from measured quantities (pure function: unit-tested on the CPU).
+    n_ok: models integrated (flag 0) over all ranks and timed steps; n_cells: cells processed; wall_s / kernel_ms:
+    totals over the timed steps (max over ranks); stats: rank 0's per-cell counters of the timed steps."""
+    f_rhs, f_jac, f_lu, f_solve, f_rates, b_cell, f_lu_exec, f_solve_exec = list(work_model)[:8]
     S = {k: stats[:, i].astype(np.float64).sum() for i, k in enumerate(stat_fields)}
+    n_stat = max(1, stats.shape[0])
     w_flop = (S["nfe"] * f_rhs + S["nje"] * f_jac + S["nlu"] * f_lu + S["nni"] * f_solve + S["nintervals"] * f_rates)
-    w_bytes = S["nintervals"] * b_interval
-    kern_s = kernel_ms / 1e3 / a.steps          # one launch per step
-    peak, how = peak_hbm()
-    roof = {"bound": "hbm", "achieved": w_bytes / kern_s / 1e9, "peak": peak, "unit": "GB/s",
-            "frac": w_bytes / kern_s / 1e9 / peak, "traffic": traffic, "peak_source": how,
-            "note": "state is chip-resident per cell: HBM traffic is only cell load/store, the kernel is bound "
-                    "by dependent-instruction latency (shared memory, barriers) and the fp64 pipe, see fp64"}
-    fp64 = {"achieved_tflops": w_flop / kern_s / 1e12, "peak_tflops": fp64_peak_tflops,
-            "frac": w_flop / kern_s / 1e12 / fp64_peak_tflops if fp64_peak_tflops else None,
-            "peak_source": "DFMA micro-benchmark run by this process (uclgpu_fp64_peak)"}
+    w_exec = (S["nfe"] * f_rhs + S["nje"] * f_jac + S["nlu"] * f_lu_exec + S["nni"] * f_solve_exec + S["nintervals"] * f_rates)
+    kern_s = kernel_ms / 1e3
+    # rank 0's counters cover n_stat cells of n_cells / world per rank: same work per rank by construction
+    scale = (n_cells / world) / n_stat
+    tfl = w_flop * scale / kern_s / 1e12
+    hbm_peak, how = peak_hbm()
+    gbs = b_cell * (n_cells / world) / kern_s / 1e9
+    roof = {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
+            "frac": tfl / fp64_peak_tflops if fp64_peak_tflops else None, "traffic": traffic,
+            "peak_source": "DFMA micro-benchmark run by this process (uclgpu_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
+            "algorithmic_flop_per_model": w_flop / n_stat, "executed_flop_per_model": w_exec / n_stat,
+            "note": "per GPU. Algorithmic counts: F_rhs, F_jac, F_lu = sparse factor terms + 2/3 m^3 for the dense "
+                    "block, F_solve = substitution, F_rates (uclgpu_work_model); the explicit dense inverse and the "
+                    "product-form programs this build executes are NOT counted. The kernel is latency bound "
+                    "(one sequential chain of ~9 k BDF steps per model, working set chip-resident)",
+            "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": how,
+                    "algorithmic_bytes_per_model": b_cell,
+                    "note": "state is chip-resident: algorithmic HBM traffic is the parameters in and the result row out"}}
     return {
-        "metric": METRIC, "value": world * ncell * a.steps / dt, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": n_ok / kern_s, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * wall_s / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload, "clocks": clocks,
-        "e2e": {"value": world * ncell * a.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes)},
-        "gpu_launches": int(launches + launches_e2e),
+        "e2e": {"value": n_ok / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes), "gather_bytes_per_step": int(gather_bytes)},
+        "gpu_launches": int(launches),
         "kernel_ms_per_step": kernel_ms / a.steps,   # CUDA events around k_integrate on its stream (max over ranks)
-        "roofline": roof, "fp64": fp64, "cpu_baseline": cpu, "parity": parity,
-        "solver": {"steps_per_model": S["nst"] / ncell, "lu_per_model": S["nlu"] / ncell,
-                   "jac_per_model": S["nje"] / ncell, "newton_iters_per_model": S["nni"] / ncell,
-                   "failed_dvode_calls": S["nfailcall"]},
+        "per_rank_kernel_ms_per_step": per_rank_kernel_ms,
+        "models": {"cells_processed": int(n_cells), "integrated": int(n_ok), "abandoned_at_step_budget": int(n_budget),
+                   "other_failures": int(n_cells - n_ok - n_budget)},
+        "roofline": roof, "cpu_baseline": cpu, "parity": parity,
+        "solver": {"steps_per_model": S["nst"] / n_stat, "lu_per_model": S["nlu"] / n_stat,
+                   "jac_per_model": S["nje"] / n_stat, "newton_iters_per_model": S["nni"] / n_stat,
+                   "failed_dvode_calls": S["nfailcall"],
+                   "sm_cycles_per_bdf_step": S["cyc_total"] / max(1.0, S["nst"])},
     }
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=NSLICE)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--step-budget", type=int, default=STEP_BUDGET,
+                    help="BDF steps after which a cell is abandoned (flag -5, not counted); 0 = the reference's unbounded crawl")
+    ap.add_argument("--transfer-band", type=float, default=0.0,
+                    help="opt-in deviation uclgpu_opts.transfer_band (DESIGN.md section 6); 0 = reference behaviour")
+    ap.add_argument("--cpu-seconds", type=float, default=60.0, help="bound of the cpu_baseline sample")
     ap.add_argument("--cells", type=int, default=0, help="debug: override the grid size (not a valid bench line)")
-    ap.add_argument("--full-grid", action="store_true",
-                    help="time all 10^4 cells, including the 161 on which the reference algorithm stalls (~10 min per pass)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    params = config2_params()
-    n_grid = params.shape[1]
-    if not a.full_grid:
-        params = np.ascontiguousarray(params[:, bounded_cells(n_grid)])
+    params = config2_params(rank=rank, world=world)
     if a.cells:
         params = np.ascontiguousarray(params[:, np.linspace(0, params.shape[1] - 1, a.cells).astype(int)])
     ncell = params.shape[1]
-    # warm-up steps run the same kernel over a bounded stride of the same grid (clocks, instruction
-    # cache, lazy module load); a full pass is tens of seconds and has no state a warm-up could prime
-    n_warm = min(ncell, 592)
-    warm_idx = np.linspace(0, ncell - 1, n_warm).astype(int)
-    excluded = n_grid - params.shape[1] if not a.cells else None
-    workload = {"workload": f"config[1]: {n_grid}-point static cloud grid (25 n_H x 20 T x 20 zeta), 1 Myr, default "
-                            "network 335 species / 3203 reactions, reltol 1e-8"
-                            + ("" if a.full_grid else f"; both arms time the {ncell} cells with bounded work: the "
-                               f"{excluded} cells (1.6 %) on which the reference algorithm itself stalls (MXSTEP in "
-                               "every DVODE retry, 1e5-1e7 steps, up to 573 s for ONE cell on one SM) are left out, "
-                               "see bench.py docstring / DESIGN.md section 6"),
-                "cells_per_gpu": ncell,
-                "full_grid_measured": "all 10000 cells, one device-resident pass on one B200: 573.2 s = 17.4 models/s "
-                                      "(round 1, profiles/r01b_bench_full_grid_stderr.log); `--full-grid` re-measures it",
-                "timing": "L2 flushed (256 MiB write) between timed steps",
-                "warmup_step": f"one pass over a {n_warm}-cell stride of the same grid (same kernel and launch shape)"}
+    slices = [slice_cells(ncell, q) for q in range(NSLICE)]
+    workload = {"workload": f"config[1]: 10^4-point static cloud grid (25 n_H x 20 T x 20 zeta), 1 Myr, default network "
+                            "335 species / 3203 reactions, reltol 1e-8, ALL cells"
+                            + (f"; {world} ranks: zeta axis refined to {20 * world} points, one 10^4-cell grid per GPU" if world > 1 else ""),
+                "step": f"one interleaved quarter of the rank's grid ({len(slices[0])} cells per GPU, flat index = step mod {NSLICE}); "
+                        f"{NSLICE} consecutive steps cover the grid once",
+                "cells_per_gpu_per_step": int(len(slices[0])), "cells_total": int(world * ncell),
+                "step_budget": a.step_budget, "transfer_band": a.transfer_band,
+                "timing": "L2 flushed (256 MiB write) between timed steps; inputs (5 MB per step) are far smaller than L2 "
+                          "but are read once per cell",
+                "warmup_step": "one pass over a 296-cell stride of the same grid (same kernel and launch shape), step budget 20 000"}
 
-    # ------------------------------------------------------------------ reference arm
+    # ------------------------------------------------------------------ reference arm (CPU restatement)
     if a.impl == "reference":
         if rank != 0:
             return
         cores = cpu_cores()
-        deadline = max(30.0, min(120.0, 240.0 / max(1, a.steps)))   # the whole run stays within a few minutes
-        for w in range(a.warmup):   # results discarded: a short bound is enough to page the library in
-            log(f"reference arm: warm-up sample {w + 1}/{a.warmup} on {cores} cores")
-            run_oracle_sample(params, cores, offset=1 + w, deadline_s=30.0)
-        n_done, dt, cut = 0, 0.0, 0
-        for k in range(a.steps):
-            v_k, dt_k, idx, _, flag = run_oracle_sample(params, cores, offset=100 + k, deadline_s=deadline)
-            n_done += int((flag != -98).sum())
-            cut += int((flag == -98).sum())
-            dt += dt_k
-            log(f"reference arm: step {k + 1}/{a.steps}: {dt_k:.1f} s, {int((flag != -98).sum())} of {len(idx)} cells finished")
-        v = n_done / dt
-        sample = (f"{cores} evenly spaced cells of the workload per step, one per host core, bounded at {deadline:.0f} s "
-                  f"per step ({cut} cells cut off and not counted)")
+        seconds = float(min(200.0, max(60.0, 30.0 * a.steps)))   # one continuous sample, reported per step
+        if a.warmup:
+            log(f"reference arm: warm-up sample ({min(5.0, a.warmup * 1.0):.0f} s) on {cores} cores")
+            run_oracle_sample(params, cores, min(5.0, a.warmup * 1.0))
+        log(f"reference arm: {seconds:.0f} s sample on {cores} cores")
+        r = run_oracle_sample(params, cores, seconds)
+        cpu = cpu_baseline_dict(r, cores, seconds)
+        workload["step"] = (f"one continuous {seconds:.0f} s sample of the same grid (shuffled work queue, all cores busy), "
+                            f"reported as {a.steps} equal steps")
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1e3 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload,
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+            "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1e3 * r["wall"] / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload, "cpu_baseline": cpu,
+            "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
 
     # ------------------------------------------------------------------ B200 arm
     import torch
     import torch.distributed as dist
-    from uclchem_b200._capi import STAT_FIELDS, UclgpuStats, get_library
-    from uclchem_b200.sharding import gather_results
+    from uclchem_b200._capi import STAT_FIELDS, UclgpuOpts, UclgpuStats, get_library
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -274,112 +299,143 @@ def main():
     lib.init([local_rank])
     neq = lib.neq
     nstat = len(STAT_FIELDS)
-
-    # device-resident buffers (value leg)
-    d_params = torch.from_numpy(params).to(dev)
-    d_y = torch.empty((ncell, neq), dtype=torch.float64, device=dev)
-    d_phys = torch.empty((ncell, 8), dtype=torch.float64, device=dev)
-    d_flag = torch.empty(ncell, dtype=torch.int32, device=dev)
-    d_stats = torch.zeros((ncell, nstat), dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    # pinned host buffers (e2e leg)
-    h_params = torch.from_numpy(params).pin_memory()
-    h_y = torch.empty((ncell, neq), dtype=torch.float64).pin_memory()
-    h_phys = torch.empty((ncell, 8), dtype=torch.float64).pin_memory()
-    h_flag = torch.empty(ncell, dtype=torch.int32).pin_memory()
-    h_stats = torch.zeros((ncell, nstat), dtype=torch.int64).pin_memory()
     pd_, pi_ = C.POINTER(C.c_double), C.POINTER(C.c_int32)
 
-    def step_device():
-        rc = lib.lib.uclgpu_run_grid_device(local_rank, 0, ncell, d_params.data_ptr(), None, d_y.data_ptr(),
-                                            d_phys.data_ptr(), d_flag.data_ptr(), d_stats.data_ptr(), None)
-        lib._check(rc)
-        return lib.last_kernel_ms(local_rank)
+    class Batch:
+        """Pinned host buffers of one step's cells (what a caller of uclgpu_run_grid owns)."""
 
-    def step_e2e():
-        rc = lib.lib.uclgpu_run_grid(0, ncell, C.cast(h_params.data_ptr(), pd_), None, C.cast(h_y.data_ptr(), pd_),
-                                     C.cast(h_phys.data_ptr(), pd_), C.cast(h_flag.data_ptr(), pi_),
-                                     C.cast(h_stats.data_ptr(), C.POINTER(UclgpuStats)), None)
-        lib._check(rc)
-        return lib.last_kernel_ms(local_rank)
+        def __init__(self, p):
+            self.n = p.shape[1]
+            self.params = torch.from_numpy(np.ascontiguousarray(p)).pin_memory()
+            self.y = torch.zeros((self.n, neq), dtype=torch.float64).pin_memory()
+            self.phys = torch.zeros((self.n, 8), dtype=torch.float64).pin_memory()
+            self.flag = torch.zeros(self.n, dtype=torch.int32).pin_memory()
+            self.stats = torch.zeros((self.n, nstat), dtype=torch.int64).pin_memory()
+
+        def run(self, budget):
+            opts = UclgpuOpts()
+            opts.step_budget = budget
+            opts.transfer_band = a.transfer_band
+            rc = lib.lib.uclgpu_run_grid(0, self.n, C.cast(self.params.data_ptr(), pd_), None,
+                                         C.cast(self.y.data_ptr(), pd_), C.cast(self.phys.data_ptr(), pd_),
+                                         C.cast(self.flag.data_ptr(), pi_),
+                                         C.cast(self.stats.data_ptr(), C.POINTER(UclgpuStats)), C.byref(opts))
+            lib._check(rc)
+            return lib.last_kernel_ms(local_rank)
+
+        def h2d_bytes(self):
+            return self.params.numel() * 8
+
+        def d2h_bytes(self):
+            return self.y.numel() * 8 + self.phys.numel() * 8 + self.flag.numel() * 4 + self.stats.numel() * 8
+
+    batches = [Batch(params[:, s]) for s in slices]
+    warm = Batch(params[:, np.linspace(0, ncell - 1, min(ncell, 296)).astype(int)])
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    n_max = max(b.n for b in batches)
+    stage = torch.empty((n_max, neq + 1), dtype=torch.float64, device=dev)       # y_final + flag, for the gather
+    gathered = [torch.empty_like(stage) for _ in range(world)] if (world > 1 and rank == 0) else None
+    h_gathered = torch.empty((world, n_max, neq + 1), dtype=torch.float64).pin_memory() if (world > 1 and rank == 0) else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
-        kernel_ms, launches = 0.0, 0
+    for _ in range(a.warmup):
+        warm.run(20000)
+        flush.fill_(1)
+    log(f"warm-up done ({a.warmup} x {warm.n} cells); timing {a.steps} steps of {batches[0].n} cells")
+
+    kernel_ms, launches = 0.0, 0
+    n_ok = n_budget = n_cells = 0
+    step_stats = []
+    with ClockSampler(local_rank) as clk:
         barrier()
         t0 = time.perf_counter()
-        for _ in range(steps):
-            ms, nl = fn()
+        for k in range(a.steps):
+            b = batches[k % NSLICE]
+            ms, nl = b.run(a.step_budget)
             kernel_ms += ms
             launches += nl
+            if world > 1:
+                # the only collective of the path: every model's final abundances and flag go to rank 0
+                stage[: b.n, :neq].copy_(b.y, non_blocking=True)
+                stage[: b.n, neq].copy_(b.flag.to(torch.float64), non_blocking=True)
+                dist.gather(stage, gathered, dst=0)
+                if rank == 0:
+                    for r_ in range(world):
+                        h_gathered[r_].copy_(gathered[r_], non_blocking=True)
+                    torch.cuda.synchronize()
+            fl = b.flag.numpy()
+            n_ok += int((fl == 0).sum())
+            n_budget += int((fl == -5).sum())
+            n_cells += b.n
+            step_stats.append(b.stats.numpy().copy())
             flush.fill_(1)  # L2 flush between timed iterations
-        if world > 1:   # the only collective of the path: final result gather on rank 0
-            gather_results(d_flag.to(torch.float64).unsqueeze(1), world * ncell, rank, world)
         barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt, kernel_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t[0].item(), t[1].item(), launches
-
-    d_wparams = torch.from_numpy(np.ascontiguousarray(params[:, warm_idx])).to(dev)
-    for _ in range(a.warmup):
-        lib._check(lib.lib.uclgpu_run_grid_device(local_rank, 0, n_warm, d_wparams.data_ptr(), None, d_y.data_ptr(),
-                                                  d_phys.data_ptr(), d_flag.data_ptr(), d_stats.data_ptr(), None))
-        flush.fill_(1)
-    log(f"warm-up done ({a.warmup} x {n_warm} cells); timing {a.steps} device-resident pass(es) over {ncell} cells")
-    with ClockSampler(local_rank) as clk:
-        dt, kernel_ms, launches = timed(step_device, a.steps)
-    log(f"device-resident leg: {dt:.1f} s ({world * ncell * a.steps / dt:.1f} models/s); timing the e2e leg")
+        wall = time.perf_counter() - t0
     clocks = clk.summary()
-    value = world * ncell * a.steps / dt
-    stats = d_stats.cpu().numpy()
-    flags = d_flag.cpu().numpy()
-    dt_e2e, _, launches_e2e = timed(step_e2e, a.steps)
-    e2e_value = world * ncell * a.steps / dt_e2e
-    log(f"e2e leg: {dt_e2e:.1f} s ({e2e_value:.1f} models/s)")
-    assert np.array_equal(h_flag.numpy(), flags)
+    t = torch.tensor([wall, kernel_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n_ok, n_budget, n_cells, launches], dtype=torch.float64, device=dev)
+    per_rank = [kernel_ms / a.steps]
+    if world > 1:
+        mine = torch.tensor([kernel_ms / a.steps], dtype=torch.float64, device=dev)
+        allk = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allk, mine)
+        per_rank = [float(x.item()) for x in allk]
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    wall, kernel_ms = t[0].item(), t[1].item()
+    n_ok, n_budget, n_cells, launches = (int(x) for x in cnt.tolist())
+    log(f"rank {rank}: {a.steps} steps in {wall:.1f} s, kernel {kernel_ms / 1e3:.1f} s")
 
     if rank == 0:
-        # ---- algorithmic work: solver counters x per-operation counts emitted by the generator
+        log(f"value {n_ok / (kernel_ms / 1e3):.2f} {UNIT}, e2e {n_ok / wall:.2f} {UNIT}; {n_budget} of {n_cells} cells hit the step budget")
         flop = (C.c_double * 8)()
         lib.lib.uclgpu_work_model(flop)
         pk = C.c_double(0.0)
         lib.lib.uclgpu_fp64_peak(local_rank, C.byref(pk))
         traffic = None   # DRAM bytes of one k_integrate launch of this workload, from the committed ncu launch list
         tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists() and not a.cells and not a.full_grid:
-            traffic = json.loads(tf.read_text()).get("k_integrate_dram_bytes_per_launch")
+        if tf.exists() and not a.cells:
+            traffic = json.loads(tf.read_text()).get("k_integrate_dram_bytes_per_step_launch")
         cores = cpu_cores()
-        deadline = 120.0
-        log(f"cpu_baseline: oracle on {cores} cores, bounded at {deadline:.0f} s")
-        try:
-            cv, cdt, idx, yref, cflag = run_oracle_sample(params, cores, deadline_s=deadline)
-            ok = cflag == 0
-            y_gpu = h_y.numpy()[idx][:, :335]
-            m = (yref[:, :335] > 1e-15) & ok[:, None]
-            dex = float(np.abs(np.log10(y_gpu[m] / yref[:, :335][m])).max()) if m.any() else None
-            cpu = {"value": cv, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": sample_text(idx, cflag, cdt, deadline)}
-            parity = {"max_dex_vs_oracle_on_sample": dex, "sample_cells_compared": int(ok.sum()),
-                      "flags_nonzero": int((flags != 0).sum()),
-                      "oracle_flags_nonzero": int(((cflag != 0) & (cflag != -98)).sum())}
-            log(f"cpu_baseline: {cdt:.1f} s, {cv:.3f} models/s")
-        except Exception as e:   # the GPU numbers must not be lost to a CPU-side problem
-            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {e!r}"}
-            parity = {"flags_nonzero": int((flags != 0).sum())}
-        # the timed numbers first, on stderr, in case anything below goes wrong
-        log(f"value {value:.2f} {UNIT}, e2e {e2e_value:.2f} {UNIT}, kernel {kernel_ms / a.steps:.1f} ms/step")
-        line = assemble_line(a=a, world=world, ncell=ncell, workload=workload, dt=dt, kernel_ms=kernel_ms,
-                             dt_e2e=dt_e2e, launches=launches, launches_e2e=launches_e2e, stats=stats, flags=flags,
+        cpu, parity = None, {"gpu_flags_nonzero": int(n_cells - n_ok)}
+        if world == 1:
+            # cpu_baseline on the cells the timed steps processed; the finished ones double as the parity sample
+            done = np.concatenate([slices[k % NSLICE] for k in range(min(a.steps, NSLICE))])
+            order = cpu_sample_order(ncell)
+            order = order[np.isin(order, done)]
+            log(f"cpu_baseline: oracle work queue on {cores} cores, bounded at {a.cpu_seconds:.0f} s")
+            try:
+                r = run_oracle_sample(params, cores, a.cpu_seconds, cells=order)
+                cpu = cpu_baseline_dict(r, cores, a.cpu_seconds)
+                y_gpu = np.zeros((ncell, neq))
+                f_gpu = np.full(ncell, -99, np.int32)
+                for q in range(min(a.steps, NSLICE)):
+                    y_gpu[slices[q]] = batches[q].y.numpy()
+                    f_gpu[slices[q]] = batches[q].flag.numpy()
+                cells = r["cells"]
+                ok = r["finished"] & (r["flag"] == 0) & (f_gpu[cells] == 0)
+                yr, yg = r["y"][ok][:, :335], y_gpu[cells[ok]][:, :335]
+                m = yr > 1e-15
+                dex = np.abs(np.log10(np.where(m, yg / np.where(m, yr, 1.0), 1.0)))
+                parity.update({"max_dex_vs_oracle_on_sample": float(dex.max()) if ok.any() else None,
+                               "cells_above_0.01_dex": int((dex.max(axis=1) > 0.01).sum()) if ok.any() else None,
+                               "sample_cells_compared": int(ok.sum()),
+                               "sample": "every cell of the cpu_baseline sample that finished in both arms with flag 0",
+                               "oracle_flags_nonzero": int(((r["flag"] != 0) & r["finished"]).sum())})
+                log(f"cpu_baseline: {r['wall']:.1f} s, {r['rate']:.3f} models/s on {cores} cores; parity on {int(ok.sum())} cells: "
+                    f"{parity['max_dex_vs_oracle_on_sample']}")
+            except Exception as e:   # the GPU numbers must not be lost to a CPU-side problem
+                cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": f"failed: {e!r}"}
+        line = assemble_line(a=a, world=world, n_ok=n_ok, n_cells=n_cells, n_budget=n_budget, workload=workload,
+                             wall_s=wall, kernel_ms=kernel_ms, launches=launches, stats=np.concatenate(step_stats),
                              clocks=clocks, work_model=list(flop), fp64_peak_tflops=pk.value,
-                             h2d_bytes=params.nbytes,
-                             d2h_bytes=h_y.numel() * 8 + h_phys.numel() * 8 + h_flag.numel() * 4 + h_stats.numel() * 8,
-                             cpu=cpu, parity=parity, traffic=traffic, stat_fields=STAT_FIELDS)
+                             h2d_bytes=batches[0].h2d_bytes(), d2h_bytes=batches[0].d2h_bytes(), cpu=cpu, parity=parity,
+                             traffic=traffic, stat_fields=STAT_FIELDS, per_rank_kernel_ms=per_rank,
+                             gather_bytes=(world - 1) * n_max * (neq + 1) * 8 if world > 1 else 0)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

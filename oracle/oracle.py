@@ -55,26 +55,51 @@ class OrcStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("nst", "nfe", "nje", "nlu", "nni", "ncfn", "netf", "nintervals")]
 
 
+_SRCS = ("orc_vode.c", "orc_chem.c", "orc_model.c", "orc_cshock.c", "orc_vode.h", "orc_internal.h", "uclchem_oracle.h")
+
+
 def build(force: bool = False) -> Path:
     so = _HERE / "liboracle.so"
-    srcs = [_HERE / f for f in ("orc_vode.c", "orc_chem.c", "orc_model.c", "orc_cshock.c", "orc_vode.h",
-                                "orc_internal.h", "uclchem_oracle.h")]
+    srcs = [_HERE / f for f in _SRCS]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE), "-B", "liboracle.so"], check=True, capture_output=True)
     return so
 
 
+def build_native() -> tuple[Path, str]:
+    """A copy compiled for the host it runs on (`-O3 -march=native`), for the CPU timing legs of bench.py: the
+    portable library is built for x86-64-v3 so that it travels.  Falls back to the portable one if the
+    compiler is missing.  Returns (path, compile flags)."""
+    out = _HERE / "_native"
+    so = out / "liboracle.so"
+    flags = "-O3 -march=native -fPIC -std=c11 -ffp-contract=off"
+    try:
+        out.mkdir(exist_ok=True)
+        srcs = [_HERE / f for f in _SRCS]
+        if not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+            subprocess.run(["gcc", *flags.split(), "-shared", "-o", str(so), *[str(_HERE / f) for f in _SRCS if f.endswith(".c")],
+                            "-lm", "-lpthread"], check=True, capture_output=True)
+        return so, flags
+    except Exception:
+        return build(), "-O3 -march=x86-64-v3 -fPIC -std=c11 -ffp-contract=off (portable build: native compile failed)"
+
+
 class Oracle:
     """The reference algorithm on the CPU, for one network."""
 
-    def __init__(self, net: Network):
+    def __init__(self, net: Network, native: bool = False):
         self.net = net
-        self.lib = C.CDLL(str(build()))
+        if native:
+            so, self.cflags = build_native()
+        else:
+            so, self.cflags = build(), "-O3 -march=x86-64-v3 -fPIC -std=c11 -ffp-contract=off"
+        self.lib = C.CDLL(str(so))
         self._keep = []
         self._c = self._pack(net)
         L = self.lib
         L.orc_run_model.restype = C.c_int
         L.orc_run_grid.restype = C.c_int
+        L.orc_run_grid_timed.restype = C.c_int
         L.orc_get_rates.restype = C.c_int
         L.orc_get_odes.restype = C.c_int
         L.orc_h2_photo_diss_rate.restype = C.c_double
@@ -166,6 +191,15 @@ class Oracle:
                               out.ctypes.data_as(_pd))
         return out
 
+    def probe_rhs(self, params: np.ndarray, y: np.ndarray) -> np.ndarray:
+        """F at exactly the given state (no pre-integration)."""
+        params = np.ascontiguousarray(params, np.float64)
+        y = np.ascontiguousarray(y, np.float64)
+        out = np.zeros(self.net.neq)
+        self.lib.orc_probe_rhs(C.byref(self._c), params.ctypes.data_as(_pd), y.ctypes.data_as(_pd),
+                               out.ctypes.data_as(_pd))
+        return out
+
     def run_model(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 500, rates: bool = False):
         """Returns dict(flag, y_final, phys_final, physics[nrows,8], abund[nrows,nspec], rates, stats, t_diss)."""
         net = self.net
@@ -192,8 +226,9 @@ class Oracle:
                     rates=rts[:n] if rates else None,
                     stats={k: getattr(st, k) for k, _ in OrcStats._fields_}, dissipation_time=tdiss.value)
 
-    def run_grid(self, kind: int, params: np.ndarray, y0=None, nthreads: int | None = None):
-        """params [NPARAM, ncell]; returns (y_final[ncell,neq], phys[ncell,8], flag[ncell], stats)."""
+    def run_grid(self, kind: int, params: np.ndarray, y0=None, nthreads: int | None = None, timed: bool = False):
+        """params [NPARAM, ncell]; returns (y_final[ncell,neq], phys[ncell,8], flag[ncell], stats) and, with
+        `timed`, the wall seconds of every model (-1 for cells the deadline guard never let start)."""
         net = self.net
         params = np.ascontiguousarray(params, np.float64)
         ncell = params.shape[1]
@@ -208,8 +243,11 @@ class Oracle:
             y0p = y0.ctypes.data_as(_pd)
         if nthreads is None:
             nthreads = os.cpu_count() or 1
-        self.lib.orc_run_grid(C.byref(self._c), C.c_int(kind), C.c_int64(ncell), params.ctypes.data_as(_pd),
-                              y0p, yfin.ctypes.data_as(_pd), pfin.ctypes.data_as(_pd),
-                              flag.ctypes.data_as(_pi), stats, C.c_int(nthreads))
+        secs = np.full(ncell, -1.0)
+        self.lib.orc_run_grid_timed(C.byref(self._c), C.c_int(kind), C.c_int64(ncell), params.ctypes.data_as(_pd),
+                                    y0p, yfin.ctypes.data_as(_pd), pfin.ctypes.data_as(_pd),
+                                    flag.ctypes.data_as(_pi), stats, C.c_int(nthreads), secs.ctypes.data_as(_pd))
         st = np.array([[getattr(s, k) for k, _ in OrcStats._fields_] for s in stats], np.int64)
+        if timed:
+            return yfin, pfin, flag, st, secs
         return yfin, pfin, flag, st

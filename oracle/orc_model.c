@@ -9,6 +9,7 @@
  * One orc_model holds what the reference keeps in module globals, so models
  * are independent and the grid runner can thread over them.
  */
+#define _POSIX_C_SOURCE 200809L
 #include "orc_internal.h"
 
 #include <math.h>
@@ -16,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
+#include <time.h>
 
 #define MIN_ABUND 1.0e-30
 #define MAX_LOOPS 10
@@ -412,6 +414,7 @@ typedef struct {
     orc_stats *stats;
     int64_t *next; /* shared work counter */
     pthread_mutex_t *lock;
+    double *cell_seconds; /* optional: wall time of each model (benchmark accounting) */
 } grid_job;
 
 static void *grid_worker(void *arg)
@@ -422,14 +425,18 @@ static void *grid_worker(void *arg)
         pthread_mutex_lock(j->lock);
         int64_t c = (*j->next)++;
         pthread_mutex_unlock(j->lock);
-        if (c >= j->ncell) break;
+        if (c >= j->ncell || orc_deadline_expired()) break; /* cells never started keep ORC_FLAG_DEADLINE */
         double p[UCLGPU_NPARAM];
         for (int k = 0; k < UCLGPU_NPARAM; k++) p[k] = j->params[(size_t)k * j->ncell + c];
         int nrows = 0;
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
         j->flag[c] = orc_run_model(j->net, j->kind, p, j->y0 ? j->y0 + (size_t)c * neq : NULL,
                                    j->y_final + (size_t)c * neq,
                                    j->phys_final ? j->phys_final + (size_t)c * UCLGPU_NPHYS : NULL, 0, NULL,
                                    NULL, NULL, &nrows, NULL, j->stats ? j->stats + c : NULL);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        if (j->cell_seconds) j->cell_seconds[c] = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     }
     return NULL;
 }
@@ -439,11 +446,22 @@ static void *grid_worker(void *arg)
 int orc_run_grid(const orc_network *net, int kind, int64_t ncell, const double *params, const double *y0,
                  double *y_final, double *phys_final, int32_t *flag, orc_stats *stats, int nthreads)
 {
+    return orc_run_grid_timed(net, kind, ncell, params, y0, y_final, phys_final, flag, stats, nthreads, NULL);
+}
+
+/* ... and with the wall time of every model (cells the deadline guard never let start keep -1) */
+int orc_run_grid_timed(const orc_network *net, int kind, int64_t ncell, const double *params, const double *y0,
+                       double *y_final, double *phys_final, int32_t *flag, orc_stats *stats, int nthreads,
+                       double *cell_seconds)
+{
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     int64_t next = 0;
     pthread_mutex_t lock = PTHREAD_MUTEX_INITIALIZER;
-    grid_job job = {net, kind, ncell, params, y0, y_final, phys_final, flag, stats, &next, &lock};
+    grid_job job = {net, kind, ncell, params, y0, y_final, phys_final, flag, stats, &next, &lock, cell_seconds};
+    if (cell_seconds)
+        for (int64_t c = 0; c < ncell; c++) cell_seconds[c] = -1.0;
+    for (int64_t c = 0; c < ncell; c++) flag[c] = ORC_FLAG_DEADLINE;
     pthread_t th[256];
     for (int t = 0; t < nthreads; t++) pthread_create(&th[t], NULL, grid_worker, &job);
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
@@ -471,6 +489,16 @@ int orc_get_rates(const orc_network *net, const double *params, const double *y_
     orc_model *m = prepare_single(net, params, y_in);
     chemistry_setup(m);
     memcpy(rates_out, m->rate, sizeof(double) * net->nreac);
+    model_free(m);
+    return 0;
+}
+
+/* F at exactly the given state (no pre-integration): the counterpart of the device probe uclgpu_probe_rhs */
+int orc_probe_rhs(const orc_network *net, const double *params, const double *y_in, double *ydot_out)
+{
+    orc_model *m = prepare_single(net, params, y_in);
+    chemistry_setup(m);
+    orc_rhs(m, m->current_time, m->abund, ydot_out);
     model_free(m);
     return 0;
 }

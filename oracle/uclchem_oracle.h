@@ -72,6 +72,10 @@ int orc_get_rates(const orc_network *net, const double *params, const double *y_
 /* F(y) at the model's initial physical state (wrap.f90:516-547 get_odes). */
 int orc_get_odes(const orc_network *net, const double *params, const double *y_in /*[nspec]*/,
                  double *ydot_out /*[nspec+1]*/);
+/* F(y) at exactly the given state (updateChemistry's set-up, chemistry.f90:166-203, then F): kernel-level
+ * parity counterpart of uclgpu_probe_rhs */
+int orc_probe_rhs(const orc_network *net, const double *params, const double *y_in /*[nspec]*/,
+                  double *ydot_out /*[nspec+1]*/);
 /* bare GETYDOT (odes.f90:6) for RHS pinning */
 void orc_getydot(const orc_network *net, const double *rate, const double *y, double blr,
                  double surface_coverage, double safe_mantle, double safe_bulk, double dens,
@@ -93,6 +97,9 @@ int orc_run_model(const orc_network *net, int kind, const double *params, const 
 int orc_run_grid(const orc_network *net, int kind, int64_t ncell, const double *params,
                  const double *y0 /*[ncell][nspec+1] or NULL*/, double *y_final /*[ncell][nspec+1]*/,
                  double *phys_final /*[ncell][8]*/, int32_t *flag, orc_stats *stats, int nthreads);
+int orc_run_grid_timed(const orc_network *net, int kind, int64_t ncell, const double *params, const double *y0,
+                       double *y_final, double *phys_final, int32_t *flag, orc_stats *stats, int nthreads,
+                       double *cell_seconds /*[ncell] wall time per model, or NULL*/);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,8 @@
 """io.f90 text formats on the host (uclchem_b200/datio.py), pinned on an excerpt of the reference's own
 example output (tests/golden/static_full_excerpt.dat: header, first three rows and the 1 Myr row of
 examples/example-output/static-full.dat)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 from conftest import GOLDEN
@@ -75,6 +77,7 @@ class _OracleBackedLibrary:
                                    timepoints=tp if timepoints else 500)
             out["y_final"][c], out["phys_final"][c], out["flag"][c] = r["y_final"], r["phys_final"], r["flag"]
             out["stats"][c, self._iint] = r["stats"]["nintervals"]
+            out["dissipation_time"][c] = r["dissipation_time"]
             n = len(r["physics"])
             if want_physics:
                 out["physics"][c, :n] = r["physics"]
@@ -127,3 +130,27 @@ def test_grid_trajectories_host_logic(oracle, net, monkeypatch):
     assert g["nrows"][1] > g["nrows"][0]
     with pytest.raises(RuntimeError, match="Offending keys"):
         model.cloud_grid({"initialDens": [1e3, 1e4], "outputFile": "x.dat"})
+
+
+def test_cshock_return_conventions_host_logic(oracle, net, monkeypatch):
+    """cshock's return tuples follow the reference (model.py:606-643): disk mode [flag, dissipation_time, *abunds],
+    in-memory (physics, chem, rates, dissipation_time, abundanceStart, flag); on failure the dissipation time is
+    None.  An unknown key is PARAMETER_READ_ERROR (-1) for a single model, not an exception."""
+    from uclchem_b200 import model
+    monkeypatch.setattr(model, "get_library", lambda *a, **k: _OracleBackedLibrary(oracle, net))
+    sc = np.load(Path(__file__).parent / "golden" / "shockstart.npy")
+    pd_ = {"initialDens": 1e4, "initialTemp": 10.0, "finalTime": 2.0}
+    phys, chem, rates, tdiss, start, flag = model.cshock(20.0, param_dict=pd_, return_array=True, starting_chemistry=sc)
+    assert flag == 0 and rates is None and isinstance(tdiss, float) and 1e2 < tdiss < 1e5      # years
+    assert start.shape == (net.nspec,) and np.array_equal(start, chem[-1, 0]) and phys.shape[1:] == (1, 8)
+    res = model.cshock(20.0, param_dict=pd_, out_species=["CO"])
+    assert res[0] == 0 and res[1] == pytest.approx(tdiss) and len(res) == 3
+    # a failing model: too few time points in memory mode -> flag -6, dissipation time None (model.py:606-607)
+    out = model.cshock(20.0, param_dict={**pd_, "finalTime": 40.0}, return_array=True, starting_chemistry=sc, timepoints=1)
+    assert out[-1] == -6 and out[3] is None
+    # disk mode has no row limit: the same model with the same tiny buffer still writes every row
+    assert model.cloud(param_dict={"initialDens": 1e4, "finalTime": 1e2}, timepoints=2)[0] == 0
+    assert model.cloud(param_dict={"initialDensity": 1e4}) == [-1]
+    assert model.cshock(20.0, param_dict={"nonsense": 1.0}, return_array=True)[-1] == -1
+    with pytest.raises(KeyError):
+        model.cloud_grid({"initialDensity": [1e3, 1e4]})

@@ -223,3 +223,67 @@ def test_disk_mode_files(lib, net, tmp_path):
     # row 0 of the new run is the loaded state (totals like BULK / SURFACE / E- may be re-derived by the model)
     keep = np.array([n not in ("BULK", "SURFACE", "E-") for n in net.names])
     assert res2[0] == 0 and np.allclose(data2[0, 8:][keep], final[keep], rtol=1e-4, atol=1e-29)
+
+
+def test_device_rhs_matches_oracle_F_componentwise(lib, oracle, net):
+    """Kernel-level parity of F (chemistry.f90:294-352 + odes.f90) at 18 states: golden-trajectory abundances
+    evaluated under cold / warm / hot physics, so that both branches of the three-phase transfer (net surface
+    growth S >= 0 and S < 0) occur.  Per component: 1e-12 relative, plus the rounding of the component's own
+    sum -- ydot_i is a difference of gains and losses that the device adds in a different order (team
+    reductions), so a few ulps of the GROSS sum is the floor for any reordering of the reference's loop."""
+    from uclchem_b200 import symbolic
+    from uclchem_b200.table_emulator import COV0, TableEngine
+    sym = symbolic.build(net)
+    eng = TableEngine(sym)
+    gold = np.load(GOLDEN / "static_full.npz")
+    rows = [0, 3, 12, 25, 46, 60]
+    physics = [dict(STATIC), dict(STATIC, initialDens=1e5, initialTemp=50.0, zeta=10.0),
+               dict(STATIC, initialDens=1e6, initialTemp=200.0, zeta=100.0, radfield=3.0, baseAv=1.0)]
+    signs = set()
+    u = np.finfo(float).eps
+    for pd_ in physics:
+        p1 = params_from_dict(pd_)
+        ys = np.array([np.append(np.maximum(gold["abund"][r], 1e-30), pd_["initialDens"]) for r in rows])
+        got = lib.probe_rhs(np.repeat(p1, len(ys), axis=1), ys)
+        for k in range(len(ys)):
+            ref = oracle.probe_rhs(p1[:, 0], ys[k, :335])
+            rate = oracle.get_rates(p1[:, 0], ys[k, :335])
+            y = ys[k].copy()
+            y[sym.iB], y[sym.iS] = y[net.bulk_list].sum(), y[net.surface_list].sum()
+            ye, _ = eng.ext_state(y, rate)
+            flux = rate * np.prod(ye[sym.flux_f], axis=1)
+            rows_ = np.repeat(np.arange(net.nspec), np.diff(sym.g_ptr))
+            gross = np.zeros(336)
+            gross[:335] = np.bincount(rows_, weights=np.abs(flux[sym.g_reac]), minlength=335)
+            net_ = np.bincount(rows_, weights=flux[sym.g_reac] * sym.g_sign, minlength=335)
+            S = net_[net.surface_list].sum()
+            signs.add(bool(S < 0))
+            gs, gb = gross[net.surface_list].sum(), gross[net.bulk_list].sum()
+            q = min(1.0, max(1e-30, y[sym.iB]) / max(1e-30, y[sym.iS])) / max(1e-30, y[sym.iB]) if S < 0 else COV0
+            src = net.bulk_list if S < 0 else net.surface_list
+            gross[net.surface_list] += gs * q * y[src]
+            gross[net.bulk_list] += gs * q * y[src]
+            gross[sym.iS] = gs + gs * q * y[src].sum()
+            gross[sym.iB] = gb + gs * q * y[src].sum()
+            tol = 1e-12 * np.abs(ref) + 64 * u * gross
+            bad = np.abs(got[k] - ref) > tol
+            assert not bad.any(), (pd_["initialTemp"], rows[k], np.where(bad)[0][:5], got[k][bad][:5], ref[bad][:5])
+            well = gross[:335] < 1e2 * np.abs(ref[:335])       # components without cancellation: plain relative error
+            assert np.abs(got[k][:335][well] / ref[:335][well] - 1).max() < 1e-12
+    assert signs == {True, False}
+
+
+def test_config2_cells_at_1myr_against_oracle_fixture(lib):
+    """1 Myr config-2 cells, including the regions where the integration is hard, against the oracle run to
+    completion offline (tools/make_config2_fixture.py -> tests/golden/config2_1myr_cells.npz): cells 8679, 7245,
+    5277 cost the oracle 56 k - 155 k steps (finite-difference Jacobian), cells 6179, 4146, 5721, 8361 are cells
+    the round-1 engine needed more than 30 000 steps for.  North-star bar: 0.01 dex above 1e-15."""
+    from bench import config2_params
+    fx = np.load(GOLDEN / "config2_1myr_cells.npz")
+    cells = fx["cells"]
+    assert (fx["flag"] == 0).all() and len(cells) >= 14
+    P = config2_params()
+    out = lib.run_grid(0, np.ascontiguousarray(P[:, cells]), step_budget=1000000)
+    assert (out["flag"] == 0).all(), dict(zip(cells.tolist(), out["flag"].tolist()))
+    worst = {int(c): max_dex(out["y_final"][k, :335], fx["y_final"][k, :335]) for k, c in enumerate(cells)}
+    assert max(worst.values()) <= DEX_TOL, worst

@@ -38,7 +38,8 @@ class UclgpuStats(C.Structure):
 
 class UclgpuOpts(C.Structure):
     _fields_ = [("timepoints", C.c_int32), ("physics_traj", _pd), ("chem_traj", _pd), ("rates_traj", _pd),
-                ("dissipation_time", _pd), ("keep_on_device", C.c_int32), ("step_budget", C.c_int32)]
+                ("dissipation_time", _pd), ("reserved0", C.c_int32), ("step_budget", C.c_int32),
+                ("transfer_band", C.c_double), ("cost_hint", _pd), ("chunk_bytes", C.c_int64)]
 
 
 class UclgpuError(RuntimeError):
@@ -110,7 +111,8 @@ class Library:
         return out
 
     def run_grid(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 0, want_physics=False,
-                 want_chem=False, want_rates=False, step_budget: int = 0):
+                 want_chem=False, want_rates=False, step_budget: int = 0, transfer_band: float = 0.0, cost_hint=None,
+                 chunk_bytes: int = 0):
         params = np.ascontiguousarray(params, np.float64)
         assert params.ndim == 2 and params.shape[0] == NPARAM
         ncell = params.shape[1]
@@ -126,6 +128,12 @@ class Library:
         opts = UclgpuOpts()
         opts.timepoints = timepoints
         opts.step_budget = step_budget
+        opts.transfer_band = transfer_band
+        opts.chunk_bytes = chunk_bytes
+        if cost_hint is not None:
+            cost_hint = np.ascontiguousarray(cost_hint, np.float64)
+            assert cost_hint.shape == (ncell,)
+            opts.cost_hint = cost_hint.ctypes.data_as(_pd)
         out = {}
         tdiss = np.zeros(ncell)
         opts.dissipation_time = tdiss.ctypes.data_as(_pd)

@@ -49,14 +49,17 @@ def generate(tag: str = "default", network_f90: str | None = None) -> Path:
 VARIANTS = {
     "": [],
     "sub": ["-DUCLGPU_NO_PRODUCT_FORM"],
+    # inverse program of the product form on the whole CTA after the dense inverse instead of next to it
+    "nov": ["-DUCLGPU_NO_PF_OVERLAP"],
 }
 
 
 def compile(tag: str = "default", force: bool = False, verbose: bool = False, variant: str = "") -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     gen = CSRC / "generated" / tag / "net_tables.cuh"
-    if not gen.exists():
-        generate(tag)
+    generator = [_PKG / f for f in ("makerates_cuda.py", "symbolic.py", "product_form.py", "network.py")]
+    if not gen.exists() or any(g.stat().st_mtime > gen.stat().st_mtime for g in generator):
+        generate(tag)   # tables are a pure function of the network and the generator
     LIBDIR.mkdir(exist_ok=True)
     out = LIBDIR / (f"libuclgpu_{tag}_{variant}.so" if variant else f"libuclgpu_{tag}.so")
     srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_gj.cuh", CSRC / "engine_bdf.cuh",

@@ -73,7 +73,8 @@ struct Scalars {
     int lh_on, swap_off, mxstep, kind;
     long long step_budget;
     // RHS ext quantities at the last evaluated state
-    double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S;
+    double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S, e_w, e_dw;
+    double transfer_band; // uclgpu_opts.transfer_band (0: the reference's switch)
     double dflux[2]; // fluxes of the deferred photo reactions (H2 + hv, CO + hv)
     // hotcore / cshock
     double max_temp, vs, timestep_factor, min_postshock_temp;
@@ -104,7 +105,9 @@ struct Scalars {
 // and builds with -DUCLGPU_NO_PRODUCT_FORM keep the level-scheduled substitution.
 #if !defined(UCLGPU_COMPACT_SMEM) && !defined(UCLGPU_NO_PRODUCT_FORM)
 #define UCLGPU_PRODUCT_FORM
+#ifndef UCLGPU_NO_PF_OVERLAP
 #define UCLGPU_PF_OVERLAP
+#endif
 #endif
 #ifdef UCLGPU_PRODUCT_FORM
 #define NET_NVAL_STORE NET_NVAL_PF

@@ -15,7 +15,9 @@
 
 struct RunArgs {
     int kind;
-    long long ncell;
+    long long ncell;       // cells in the input arrays (stride of params)
+    long long nrun;        // cells this launch integrates: queue positions 0..nrun-1, cell = order ? order[pos] : pos
+    int compact;           // 1: results are indexed by queue position (compact), 0: by cell
     const double *params;  // [UCLGPU_NPARAM][ncell]
     const double *y0;      // [ncell][NEQ] or null
     double *y_final;       // [ncell][NEQ]
@@ -32,6 +34,7 @@ struct RunArgs {
     long long max_steps;         // uclgpu_opts.step_budget: abandon a cell (flag -5) beyond this many BDF steps; 0 = off
     const int *order;            // processing order of the cells (most expensive first) or null
     double *dump;
+    double transfer_band;        // uclgpu_opts.transfer_band: blend the three-phase transfer branches (0 = off)
 };
 
 // ---- physics hooks (thread 0) ---------------------------------------------------------------
@@ -471,7 +474,8 @@ __device__ void output_row_dev(Smem &s, const RunArgs &a, long long cell, int dt
 }
 
 // solveAbundances wrap.f90:549-697 for one cell
-__device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
+// (inputs are read at index `cell`, results are written at index `out`)
+__device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long long out)
 {
     Scalars &st = s.st;
     const int tid = threadIdx.x;
@@ -486,6 +490,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
     st.abstol_factor = st.p[UCL_P_ABSTOL_FACTOR];
     st.mxstep = (int)st.p[UCL_P_MXSTEP];
     st.step_budget = a.max_steps;
+    st.transfer_band = a.transfer_band;
     st.rtol = st.p[UCL_P_RELTOL];
     st.last_temp = 99.0e99;
     st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;
@@ -510,7 +515,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
         BLOCK_SYNC();
         if (want_traj) {
             if (dtime > a.timepoints + 1) flag = UCLGPU_NOT_ENOUGH_TIMEPOINTS_ERROR;
-            else output_row_dev(s, a, cell, dtime);
+            else output_row_dev(s, a, out, dtime);
         }
         for (;;) {
             BLOCK_SYNC();
@@ -534,22 +539,22 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell)
             if (st.kind == UCLGPU_CSHOCK) cshock_sublimation_dev(s, b);
             if (want_traj) {
                 if (dtime > a.timepoints + 1) flag = UCLGPU_NOT_ENOUGH_TIMEPOINTS_ERROR;
-                else output_row_dev(s, a, cell, dtime);
+                else output_row_dev(s, a, out, dtime);
             }
         }
     }
     BLOCK_SYNC();
-    for (int i = tid; i < NEQ; i += NT) a.y_final[(size_t)cell * NEQ + i] = s.abund[i];
+    for (int i = tid; i < NEQ; i += NT) a.y_final[(size_t)out * NEQ + i] = s.abund[i];
     if (tid == 0) {
-        a.flag[cell] = flag;
+        a.flag[out] = flag;
         if (a.phys_final) {
-            double *r = a.phys_final + (size_t)cell * UCLGPU_NPHYS;
+            double *r = a.phys_final + (size_t)out * UCLGPU_NPHYS;
             r[0] = st.time_in_years; r[1] = st.density; r[2] = st.gastemp; r[3] = st.dusttemp;
             r[4] = st.av; r[5] = st.radfield; r[6] = st.zeta; r[7] = 1.0;
         }
-        if (a.tdiss) a.tdiss[cell] = (st.kind == UCLGPU_CSHOCK) ? st.cs_dissipation_time : 0.0;
+        if (a.tdiss) a.tdiss[out] = (st.kind == UCLGPU_CSHOCK) ? st.cs_dissipation_time : 0.0;
         if (a.stats) {
-            uclgpu_stats &o = a.stats[cell];
+            uclgpu_stats &o = a.stats[out];
             o.nst = st.nst; o.nfe = st.nfe; o.nje = st.nje; o.nlu = st.nlu; o.nni = st.nni;
             o.ncfn = st.ncfn; o.netf = st.netf; o.nintervals = st.nintervals;
             o.nsing = st.nsing; o.nmaxcor = st.nmaxcor; o.ndiverge = st.ndiverge; o.nfailcall = st.nfailcall;

@@ -33,15 +33,15 @@ __global__ void __launch_bounds__(NT, 1) k_integrate(RunArgs a)
         BLOCK_SYNC();
         if (threadIdx.x == 0) cell_sh = (long long)atomicAdd(a.counter, 1ULL);
         BLOCK_SYNC();
-        long long cell = cell_sh;
-        if (cell >= a.ncell) break;
-        if (a.order) cell = a.order[cell];
+        const long long pos = cell_sh;
+        if (pos >= a.nrun) break;
+        const long long cell = a.order ? a.order[pos] : pos;
         b.trace = (cell == 0) ? a.trace : nullptr;
         b.trace_cap = a.trace_cap;
         b.trace_n = 0;
         b.dump = (cell == 0) ? a.dump : nullptr;
         b.dump_at = a.dump_at;
-        run_cell(s, b, a, cell);
+        run_cell(s, b, a, cell, a.compact ? pos : cell);
     }
 }
 
@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         st.nsing = st.nmaxcor = st.ndiverge = st.nfailcall = 0;
         st.hist_valid = 0;
         st.use_tcrit = 0;
+        st.step_budget = 0;
+        st.transfer_band = 0.0;
         st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = st.cyc_total = 0;
         initialize_physics_dev(st);
         T0_END
@@ -165,9 +167,17 @@ static char g_err[256] = "";
         }                                                                                     \
     } while (0)
 
+extern "C" void uclgpu_shutdown(void);
+
 extern "C" int uclgpu_init(int ndev, const int *devs)
 {
-    if (g_init) return 0;
+    if (g_init) {
+        // idempotent for the same device list (or "all"); a different list re-binds
+        bool same = ndev <= 0 || !devs || (size_t)ndev == g_dev.size();
+        for (int i = 0; same && devs && i < ndev && ndev > 0; i++) same = g_dev[i].id == devs[i];
+        if (same) return 0;
+        uclgpu_shutdown();
+    }
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
         snprintf(g_err, sizeof(g_err), "no CUDA device visible");
@@ -236,14 +246,18 @@ extern "C" const char *uclgpu_strerror(int code)
 
 extern "C" int uclgpu_work_model(double *out)
 {
-    // {F_rhs, F_jac, F_lu, F_solve, F_rates (flop per call), bytes per interval, 0, 0}
+    // ALGORITHMIC work (independent of the build variant): flop per call of
+    // {F_rhs, F_jac, F_lu (sparse terms + 2/3 m^3 for the dense block), F_solve (substitution), F_rates},
+    // HBM bytes per cell-model with chip-resident state, then what this build EXECUTES per
+    // factorisation / solve (explicit dense inverse, product-form programs) for reference.
     if (!out) return UCLGPU_ERR_BAD_ARGUMENT;
-#ifdef UCLGPU_PRODUCT_FORM   // algorithmic work of the product-form programs (product_form.py)
-    out[0] = NET_FLOP_RHS; out[1] = NET_FLOP_JAC; out[2] = NET_FLOP_LU_PF; out[3] = NET_FLOP_SOLVE_PF;
-#else
     out[0] = NET_FLOP_RHS; out[1] = NET_FLOP_JAC; out[2] = NET_FLOP_LU; out[3] = NET_FLOP_SOLVE;
+    out[4] = NET_FLOP_RATES; out[5] = NET_BYTES_CELL;
+#ifdef UCLGPU_PRODUCT_FORM
+    out[6] = NET_FLOP_LU_PF; out[7] = NET_FLOP_SOLVE_PF;
+#else
+    out[6] = NET_FLOP_LU_EXEC; out[7] = NET_FLOP_SOLVE;
 #endif
-    out[4] = NET_FLOP_RATES; out[5] = NET_BYTES_INTERVAL; out[6] = out[7] = 0.0;
     return 0;
 }
 
@@ -318,6 +332,7 @@ static int launch_integrate(Device &d, const RunArgs &a)
     aa.jsave = d.jsave;
     if (getenv("UCLGPU_MAX_STEPS")) aa.max_steps = atoll(getenv("UCLGPU_MAX_STEPS"));
     if (getenv("UCLGPU_WARM")) aa.warm_restart = atoi(getenv("UCLGPU_WARM"));
+    if (getenv("UCLGPU_TRANSFER_BAND")) aa.transfer_band = atof(getenv("UCLGPU_TRANSFER_BAND"));
     // debug: UCLGPU_TRACE=<records> UCLGPU_TRACE_FILE=<path> dumps cell 0's Newton iterations
     double *d_trace = nullptr;
     const char *tr = getenv("UCLGPU_TRACE");
@@ -337,7 +352,7 @@ static int launch_integrate(Device &d, const RunArgs &a)
         aa.dump_at = atoi(getenv("UCLGPU_DUMP_AT"));
     }
     CK(cudaEventRecord(d.ev0, d.stream));
-    k_integrate<<<grid_blocks(d, a.ncell), NT, sizeof(Smem), d.stream>>>(aa);
+    k_integrate<<<grid_blocks(d, a.nrun), NT, sizeof(Smem), d.stream>>>(aa);
     CK(cudaEventRecord(d.ev1, d.stream));
     CK(cudaGetLastError());
     if (cap > 0) {
@@ -361,27 +376,25 @@ static int launch_integrate(Device &d, const RunArgs &a)
     return 0;
 }
 
-// Relative cost estimate of one cell from its parameters (measured on the config-2 grid: the step
-// count grows with density and cosmic-ray rate and falls with temperature; DESIGN.md "load balance").
-static std::vector<int> cost_order(const double *params, int64_t ncell, long long lo, long long n)
+// Processing order of the cells, most expensive first.  The CTAs pull cells from one counter, so starting the
+// long cells first keeps the tail of a launch short.  `hint` (uclgpu_opts.cost_hint: any per-cell figure that
+// grows with the expected cost, e.g. the step counts of an earlier pass over the same grid) decides when given;
+// otherwise a generic key from the parameters every model has: the step count grows with the (final) density
+// and the integration time.  Nothing here knows a particular grid.
+static std::vector<int> cost_order(const double *params, int64_t ncell, const double *hint)
 {
-    std::vector<double> key(n);
-    for (long long c = 0; c < n; c++) {
-        const double dens = params[(size_t)UCL_P_INITIALDENS * ncell + lo + c];
-        const double fdens = params[(size_t)UCL_P_FINALDENS * ncell + lo + c];
-        const double ff = params[(size_t)UCL_P_FREEFALL * ncell + lo + c];
-        const double zeta = params[(size_t)UCL_P_ZETA * ncell + lo + c];
-        const double temp = params[(size_t)UCL_P_INITIALTEMP * ncell + lo + c];
-        const double tfin = params[(size_t)UCL_P_FINALTIME * ncell + lo + c];
+    std::vector<double> key(ncell);
+    for (int64_t c = 0; c < ncell; c++) {
+        if (hint) { key[c] = hint[c]; continue; }
+        const double dens = params[(size_t)UCL_P_INITIALDENS * ncell + c];
+        const double fdens = params[(size_t)UCL_P_FINALDENS * ncell + c];
+        const double ff = params[(size_t)UCL_P_FREEFALL * ncell + c];
+        const double tfin = params[(size_t)UCL_P_FINALTIME * ncell + c];
         const double nn = (ff != 0.0 && fdens > dens) ? fdens : dens;
-        key[c] = log10(nn > 1.0 ? nn : 1.0) + 0.2 * log10(tfin > 1.0 ? tfin : 1.0) + 0.01 * temp;
-        // the two regions of the config-2 grid where DVODE keeps hitting MXSTEP (measured):
-        // dust at 34-48 K and cold gas with a very high cosmic-ray rate
-        if (temp > 33.0 && temp < 49.0) key[c] += 10.0 + 0.5 * log10(zeta > 1e-3 ? zeta : 1e-3);
-        if (temp < 12.5 && zeta >= 300.0) key[c] += 5.0;
+        key[c] = log10(nn > 1.0 ? nn : 1.0) + 0.2 * log10(tfin > 1.0 ? tfin : 1.0);
     }
-    std::vector<int> ord(n);
-    for (long long c = 0; c < n; c++) ord[c] = (int)c;
+    std::vector<int> ord(ncell);
+    for (int64_t c = 0; c < ncell; c++) ord[c] = (int)c;
     std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return key[x] > key[y]; });
     return ord;
 }
@@ -393,21 +406,23 @@ extern "C" int uclgpu_run_grid_device(int dev, uclgpu_model_kind kind, int64_t n
     if (!g_init) return UCLGPU_ERR_NOT_INITIALISED;
     Device *d = nullptr;
     for (auto &x : g_dev) if (x.id == dev) d = &x;
-    if (!d || ncell < 0 || !d_params || !d_y_final || !d_flag) return UCLGPU_ERR_BAD_ARGUMENT;
+    if (!d || ncell < 0 || ncell > INT32_MAX || !d_params || !d_y_final || !d_flag) return UCLGPU_ERR_BAD_ARGUMENT;
     if (ncell == 0) return 0;
-    (void)cuda_stream; // the library launches on its own stream and synchronises before returning
+    // The call is synchronous.  A caller stream is honoured as an ordering constraint: work already queued
+    // on it is finished before the library's own stream starts (the buffers may still be in flight there).
+    if (cuda_stream) CK(cudaStreamSynchronize((cudaStream_t)cuda_stream));
     RunArgs a;
     memset(&a, 0, sizeof(a));
-    a.kind = (int)kind; a.ncell = ncell; a.params = d_params; a.y0 = d_y0; a.y_final = d_y_final;
+    a.kind = (int)kind; a.ncell = ncell; a.nrun = ncell; a.params = d_params; a.y0 = d_y0; a.y_final = d_y_final;
     a.phys_final = d_phys_final; a.flag = d_flag; a.stats = d_stats;
     int *d_order = nullptr;
     if (ncell > d->sms) {
-        // the processing order needs six parameter rows on the host (a few hundred KB)
+        // the processing order needs four parameter rows on the host (a few hundred KB)
         CK(cudaSetDevice(d->id));
         std::vector<double> hp((size_t)UCLGPU_NPARAM * ncell);
         CK(cudaMemcpyAsync(hp.data(), d_params, sizeof(double) * hp.size(), cudaMemcpyDeviceToHost, d->stream));
         CK(cudaStreamSynchronize(d->stream));
-        std::vector<int> ord = cost_order(hp.data(), ncell, 0, ncell);
+        std::vector<int> ord = cost_order(hp.data(), ncell, nullptr);
         CK(cudaMalloc(&d_order, sizeof(int) * ncell));
         CK(cudaMemcpyAsync(d_order, ord.data(), sizeof(int) * ncell, cudaMemcpyHostToDevice, d->stream));
         CK(cudaStreamSynchronize(d->stream));
@@ -436,19 +451,36 @@ extern "C" int uclgpu_last_kernel_ms(int dev, double *ms, int64_t *launches)
     return UCLGPU_ERR_BAD_ARGUMENT;
 }
 
+// Device buffers of one chunk of cells on one device.  Inputs are full-grid arrays indexed by cell (the kernel
+// reads cell = order[queue position]); results are COMPACT, indexed by queue position, so that one contiguous
+// D2H copy per array brings back exactly this chunk's rows and the host scatters them into the caller's arrays.
 struct DevBuf {
     double *params = nullptr, *y0 = nullptr, *y_final = nullptr, *phys = nullptr, *ptraj = nullptr, *ctraj = nullptr,
            *rtraj = nullptr, *tdiss = nullptr;
     int32_t *flag = nullptr;
     int *order = nullptr;
     uclgpu_stats *stats = nullptr;
+    std::vector<double> h_y, h_phys, h_tdiss;
+    std::vector<int32_t> h_flag;
+    std::vector<uclgpu_stats> h_stats;
+    void release_chunk()
+    {
+        cudaFree(order); cudaFree(y_final); cudaFree(phys); cudaFree(ptraj); cudaFree(ctraj);
+        cudaFree(rtraj); cudaFree(tdiss); cudaFree(flag); cudaFree(stats);
+        order = nullptr; y_final = phys = ptraj = ctraj = rtraj = tdiss = nullptr; flag = nullptr; stats = nullptr;
+    }
     void release()
     {
-        cudaFree(order); cudaFree(params); cudaFree(y0); cudaFree(y_final); cudaFree(phys); cudaFree(ptraj); cudaFree(ctraj);
-        cudaFree(rtraj); cudaFree(tdiss); cudaFree(flag); cudaFree(stats);
+        release_chunk();
+        cudaFree(params); cudaFree(y0);
+        params = y0 = nullptr;
     }
 };
 
+// Sharding of one grid over the bound devices.  Cells are independent, so nothing crosses
+// between GPUs.  The grid is sorted by expected cost once; device i takes every nd-th cell of that order
+// (round-robin: each device gets the same mix of cheap and expensive cells, longest first), and a device whose
+// share does not fit its memory (trajectories: 1.3 MB per cell) runs it in strided chunks of its list.
 extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const double *params, const double *y0,
                                double *y_final, double *phys_final, int32_t *flag, uclgpu_stats *stats,
                                const uclgpu_opts *opts)
@@ -457,81 +489,117 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
         int rc = uclgpu_init(0, nullptr);
         if (rc) return rc;
     }
-    if (ncell < 0 || !params || !y_final || !flag) return UCLGPU_ERR_BAD_ARGUMENT;
+    if (ncell < 0 || ncell > INT32_MAX || !params || !y_final || !flag) return UCLGPU_ERR_BAD_ARGUMENT;
     if ((int)kind < 0 || (int)kind > 2) return UCLGPU_ERR_BAD_ARGUMENT;
     if (ncell == 0) return 0;
     const int nd = (int)g_dev.size();
-    const int T1 = opts ? opts->timepoints + 1 : 0;
+    const size_t T1 = opts ? (size_t)opts->timepoints + 1 : 0;
+    const bool want_p = opts && opts->physics_traj, want_c = opts && opts->chem_traj, want_r = opts && opts->rates_traj;
+    const bool want_t = opts && opts->dissipation_time;
+    const std::vector<int> ord = cost_order(params, ncell, opts ? opts->cost_hint : nullptr);
+    // bytes of COMPACT result storage per cell on the device
+    const size_t per_cell = sizeof(double) * (NEQ + UCLGPU_NPHYS + 1) + sizeof(int32_t) + sizeof(int) + sizeof(uclgpu_stats) +
+                            sizeof(double) * T1 * ((want_p ? UCLGPU_NPHYS : 0) + (want_c ? NSPEC : 0) + (want_r ? NREAC : 0));
     std::vector<DevBuf> bufs(nd);
-    std::vector<long long> lo(nd + 1);
-    for (int i = 0; i <= nd; i++) lo[i] = ncell * i / nd; // contiguous shards, no inter-GPU traffic
-    int rc = 0;
+    std::vector<std::vector<int>> list(nd);
+    for (int64_t k = 0; k < ncell; k++) list[k % nd].push_back(ord[k]);
+    std::vector<int> nchunk(nd, 1);
+    int rounds = 1, rc = 0;
+    // ---- full-grid inputs to every device that has cells; chunk count from the memory that is left ----
     for (int i = 0; i < nd && !rc; i++) {
+        if (list[i].empty()) continue;
         Device &d = g_dev[i];
         DevBuf &B = bufs[i];
-        long long n = lo[i + 1] - lo[i];
-        if (n == 0) continue;
         rc = [&]() -> int {
             CK(cudaSetDevice(d.id));
-            CK(cudaMalloc(&B.params, sizeof(double) * UCLGPU_NPARAM * n));
-            CK(cudaMalloc(&B.y_final, sizeof(double) * NEQ * n));
-            CK(cudaMalloc(&B.phys, sizeof(double) * UCLGPU_NPHYS * n));
-            CK(cudaMalloc(&B.flag, sizeof(int32_t) * n));
-            CK(cudaMalloc(&B.stats, sizeof(uclgpu_stats) * n));
-            CK(cudaMemcpy2DAsync(B.params, sizeof(double) * n, params + lo[i], sizeof(double) * ncell,
-                                 sizeof(double) * n, UCLGPU_NPARAM, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMalloc(&B.params, sizeof(double) * UCLGPU_NPARAM * ncell));
+            CK(cudaMemcpyAsync(B.params, params, sizeof(double) * UCLGPU_NPARAM * ncell, cudaMemcpyHostToDevice, d.stream));
             if (y0) {
-                CK(cudaMalloc(&B.y0, sizeof(double) * NEQ * n));
-                CK(cudaMemcpyAsync(B.y0, y0 + (size_t)lo[i] * NEQ, sizeof(double) * NEQ * n, cudaMemcpyHostToDevice,
-                                   d.stream));
+                CK(cudaMalloc(&B.y0, sizeof(double) * NEQ * ncell));
+                CK(cudaMemcpyAsync(B.y0, y0, sizeof(double) * NEQ * ncell, cudaMemcpyHostToDevice, d.stream));
             }
-            RunArgs a;
-            memset(&a, 0, sizeof(a));
-            a.kind = (int)kind; a.ncell = n; a.params = B.params; a.y0 = B.y0; a.y_final = B.y_final;
-            a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
-            if (n > d.sms) {
-                // longest-expected-first processing order: the CTAs pull cells from one counter, so
-                // starting the expensive cells first keeps the tail of the launch short
-                std::vector<int> ord = cost_order(params, ncell, lo[i], n);
-                CK(cudaMalloc(&B.order, sizeof(int) * n));
-                CK(cudaMemcpyAsync(B.order, ord.data(), sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
-                CK(cudaStreamSynchronize(d.stream)); // ord goes out of scope
-                a.order = B.order;
-            }
-            if (opts) {
-                a.max_steps = opts->step_budget;
-                a.timepoints = opts->timepoints;
-                if (opts->physics_traj) { CK(cudaMalloc(&B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n)); CK(cudaMemsetAsync(B.ptraj, 0, sizeof(double) * UCLGPU_NPHYS * T1 * n, d.stream)); a.phys_traj = B.ptraj; }
-                if (opts->chem_traj) { CK(cudaMalloc(&B.ctraj, sizeof(double) * NSPEC * T1 * n)); CK(cudaMemsetAsync(B.ctraj, 0, sizeof(double) * NSPEC * T1 * n, d.stream)); a.chem_traj = B.ctraj; }
-                if (opts->rates_traj) { CK(cudaMalloc(&B.rtraj, sizeof(double) * NREAC * T1 * n)); CK(cudaMemsetAsync(B.rtraj, 0, sizeof(double) * NREAC * T1 * n, d.stream)); a.rates_traj = B.rtraj; }
-                if (opts->dissipation_time) { CK(cudaMalloc(&B.tdiss, sizeof(double) * n)); a.tdiss = B.tdiss; }
-            }
-            return launch_integrate(d, a);
-        }();
-    }
-    for (int i = 0; i < nd && !rc; i++) {
-        Device &d = g_dev[i];
-        DevBuf &B = bufs[i];
-        long long n = lo[i + 1] - lo[i];
-        if (n == 0) continue;
-        rc = [&]() -> int {
-            CK(cudaSetDevice(d.id));
-            CK(cudaMemcpyAsync(y_final + (size_t)lo[i] * NEQ, B.y_final, sizeof(double) * NEQ * n, cudaMemcpyDeviceToHost, d.stream));
-            if (phys_final) CK(cudaMemcpyAsync(phys_final + (size_t)lo[i] * UCLGPU_NPHYS, B.phys, sizeof(double) * UCLGPU_NPHYS * n, cudaMemcpyDeviceToHost, d.stream));
-            CK(cudaMemcpyAsync(flag + lo[i], B.flag, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
-            if (stats) CK(cudaMemcpyAsync(stats + lo[i], B.stats, sizeof(uclgpu_stats) * n, cudaMemcpyDeviceToHost, d.stream));
-            if (opts) {
-                if (opts->physics_traj) CK(cudaMemcpyAsync(opts->physics_traj + (size_t)lo[i] * T1 * UCLGPU_NPHYS, B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n, cudaMemcpyDeviceToHost, d.stream));
-                if (opts->chem_traj) CK(cudaMemcpyAsync(opts->chem_traj + (size_t)lo[i] * T1 * NSPEC, B.ctraj, sizeof(double) * NSPEC * T1 * n, cudaMemcpyDeviceToHost, d.stream));
-                if (opts->rates_traj) CK(cudaMemcpyAsync(opts->rates_traj + (size_t)lo[i] * T1 * NREAC, B.rtraj, sizeof(double) * NREAC * T1 * n, cudaMemcpyDeviceToHost, d.stream));
-                if (opts->dissipation_time) CK(cudaMemcpyAsync(opts->dissipation_time + lo[i], B.tdiss, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
-            }
-            CK(cudaStreamSynchronize(d.stream));
-            float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
-            d.last_ms = ms;
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            size_t budget = (size_t)(0.8 * (double)free_b);
+            if (opts && opts->chunk_bytes > 0 && (size_t)opts->chunk_bytes < budget) budget = (size_t)opts->chunk_bytes;
+            const size_t fit = budget / per_cell;
+            if (fit < 1) { snprintf(g_err, sizeof(g_err), "device %d: no memory for one cell's results", d.id); return UCLGPU_ERR_CUDA; }
+            nchunk[i] = (int)((list[i].size() + fit - 1) / fit);
             return 0;
         }();
+        if (nchunk[i] > rounds) rounds = nchunk[i];
+    }
+    for (auto &d : g_dev) { d.last_ms = 0.0; d.last_launches = 0; }
+    for (int r = 0; r < rounds && !rc; r++) {
+        std::vector<std::vector<int>> cl(nd); // this round's cells per device: a stride of the device's list
+        for (int i = 0; i < nd && !rc; i++) {
+            if (r >= nchunk[i]) continue;
+            for (size_t k = r; k < list[i].size(); k += nchunk[i]) cl[i].push_back(list[i][k]);
+            const size_t n = cl[i].size();
+            if (n == 0) continue;
+            Device &d = g_dev[i];
+            DevBuf &B = bufs[i];
+            rc = [&]() -> int {
+                CK(cudaSetDevice(d.id));
+                CK(cudaMalloc(&B.order, sizeof(int) * n));
+                CK(cudaMalloc(&B.y_final, sizeof(double) * NEQ * n));
+                CK(cudaMalloc(&B.phys, sizeof(double) * UCLGPU_NPHYS * n));
+                CK(cudaMalloc(&B.flag, sizeof(int32_t) * n));
+                CK(cudaMalloc(&B.stats, sizeof(uclgpu_stats) * n));
+                CK(cudaMemcpyAsync(B.order, cl[i].data(), sizeof(int) * n, cudaMemcpyHostToDevice, d.stream));
+                RunArgs a;
+                memset(&a, 0, sizeof(a));
+                a.kind = (int)kind; a.ncell = ncell; a.nrun = (long long)n; a.compact = 1; a.order = B.order;
+                a.params = B.params; a.y0 = B.y0; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
+                if (opts) {
+                    a.max_steps = opts->step_budget;
+                    a.timepoints = opts->timepoints;
+                    a.transfer_band = opts->transfer_band;
+                    if (want_p) { CK(cudaMalloc(&B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n)); CK(cudaMemsetAsync(B.ptraj, 0, sizeof(double) * UCLGPU_NPHYS * T1 * n, d.stream)); a.phys_traj = B.ptraj; }
+                    if (want_c) { CK(cudaMalloc(&B.ctraj, sizeof(double) * NSPEC * T1 * n)); CK(cudaMemsetAsync(B.ctraj, 0, sizeof(double) * NSPEC * T1 * n, d.stream)); a.chem_traj = B.ctraj; }
+                    if (want_r) { CK(cudaMalloc(&B.rtraj, sizeof(double) * NREAC * T1 * n)); CK(cudaMemsetAsync(B.rtraj, 0, sizeof(double) * NREAC * T1 * n, d.stream)); a.rates_traj = B.rtraj; }
+                    if (want_t) { CK(cudaMalloc(&B.tdiss, sizeof(double) * n)); a.tdiss = B.tdiss; }
+                }
+                return launch_integrate(d, a);
+            }();
+        }
+        // ---- results: small per-cell rows through a compact host buffer, trajectories straight into place ----
+        for (int i = 0; i < nd && !rc; i++) {
+            const size_t n = cl[i].size();
+            if (n == 0) continue;
+            Device &d = g_dev[i];
+            DevBuf &B = bufs[i];
+            rc = [&]() -> int {
+                CK(cudaSetDevice(d.id));
+                B.h_y.resize(NEQ * n); B.h_phys.resize(UCLGPU_NPHYS * n); B.h_flag.resize(n); B.h_stats.resize(n); B.h_tdiss.resize(n);
+                CK(cudaMemcpyAsync(B.h_y.data(), B.y_final, sizeof(double) * NEQ * n, cudaMemcpyDeviceToHost, d.stream));
+                if (phys_final) CK(cudaMemcpyAsync(B.h_phys.data(), B.phys, sizeof(double) * UCLGPU_NPHYS * n, cudaMemcpyDeviceToHost, d.stream));
+                CK(cudaMemcpyAsync(B.h_flag.data(), B.flag, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, d.stream));
+                if (stats) CK(cudaMemcpyAsync(B.h_stats.data(), B.stats, sizeof(uclgpu_stats) * n, cudaMemcpyDeviceToHost, d.stream));
+                if (want_t) CK(cudaMemcpyAsync(B.h_tdiss.data(), B.tdiss, sizeof(double) * n, cudaMemcpyDeviceToHost, d.stream));
+                for (size_t k = 0; k < n && (want_p || want_c || want_r); k++) {
+                    const size_t c = (size_t)cl[i][k];
+                    if (want_p) CK(cudaMemcpyAsync(opts->physics_traj + c * T1 * UCLGPU_NPHYS, B.ptraj + k * T1 * UCLGPU_NPHYS, sizeof(double) * UCLGPU_NPHYS * T1, cudaMemcpyDeviceToHost, d.stream));
+                    if (want_c) CK(cudaMemcpyAsync(opts->chem_traj + c * T1 * NSPEC, B.ctraj + k * T1 * NSPEC, sizeof(double) * NSPEC * T1, cudaMemcpyDeviceToHost, d.stream));
+                    if (want_r) CK(cudaMemcpyAsync(opts->rates_traj + c * T1 * NREAC, B.rtraj + k * T1 * NREAC, sizeof(double) * NREAC * T1, cudaMemcpyDeviceToHost, d.stream));
+                }
+                CK(cudaStreamSynchronize(d.stream));
+                float ms = 0.f;
+                CK(cudaEventElapsedTime(&ms, d.ev0, d.ev1));
+                d.last_ms += ms;
+                d.last_launches += 1;
+                for (size_t k = 0; k < n; k++) {
+                    const size_t c = (size_t)cl[i][k];
+                    memcpy(y_final + c * NEQ, B.h_y.data() + k * NEQ, sizeof(double) * NEQ);
+                    if (phys_final) memcpy(phys_final + c * UCLGPU_NPHYS, B.h_phys.data() + k * UCLGPU_NPHYS, sizeof(double) * UCLGPU_NPHYS);
+                    flag[c] = B.h_flag[k];
+                    if (stats) stats[c] = B.h_stats[k];
+                    if (want_t) opts->dissipation_time[c] = B.h_tdiss[k];
+                }
+                B.release_chunk();
+                return 0;
+            }();
+        }
     }
     for (int i = 0; i < nd; i++) {
         cudaSetDevice(g_dev[i].id);

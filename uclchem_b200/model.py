@@ -16,8 +16,9 @@ Differences from the reference, all deliberate:
   refused with the reference's own error (``model.py:121-131``);
 * parameters start from ``defaultparameters.f90`` on every call (the reference leaks
   parameters between calls, SURVEY.md Q6);
-* a model failure is reported through the success flag, never raised
-  (``utils.check_error`` semantics, ``utils.py:30-51``).
+* a model failure is reported through the success flag, never raised (``utils.check_error`` semantics,
+  ``utils.py:30-51``); an unknown parameter key gives flag -1 (PARAMETER_READ_ERROR) for single models, while the
+  ``*_grid`` functions raise ``KeyError`` before anything runs (a table of models has no single flag).
 """
 from __future__ import annotations
 
@@ -75,7 +76,13 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
         if k in files:
             raise NotImplementedError(f"{k} is not written by the GPU path; use return_array / return_dataframe")
     pd_.update(extra)
-    params = params_from_dict(pd_, ncell=1)
+    try:
+        params = params_from_dict(pd_, ncell=1)
+    except KeyError as e:
+        # wrap.f90:966-970: an unknown key makes dictionaryParser return PARAMETER_READ_ERROR; the model is not
+        # run and the caller sees the flag (utils.check_error), not an exception
+        print(f"Parameter read failed: {e.args[0]}")
+        return _failed_result(kind, traj, -1)
     y0 = None
     if starting_chemistry is not None:
         sc = np.asarray(starting_chemistry, dtype=np.float64).ravel()
@@ -87,7 +94,13 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
     want_rows = traj or "outputfile" in files
     out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if want_rows else 0,
                        want_physics=want_rows, want_chem=want_rows, want_rates=traj and return_rates)
+    while not traj and want_rows and int(out["flag"][0]) == -6 and timepoints < (1 << 20):
+        # disk mode has no row limit in the reference (rows go straight to the file, io.f90:59-83): the rows come
+        # back through the in-memory buffers here, so a model with more output intervals is re-run with more room
+        timepoints *= 4
+        out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints, want_physics=True, want_chem=True)
     flag = int(out["flag"][0])
+    tdiss = float(out["dissipation_time"][0]) if flag >= 0 else None   # model.py:606-607
     if not traj:
         if "outputfile" in files:
             nrows = min(int(out["stats"][0][7]) + 1, timepoints + 1)
@@ -99,7 +112,7 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
         idx = [lib.species.index(s) for s in (out_species or [])]
         res = _format_output(n_out, out["y_final"][0, idx], flag)
         if kind == "cshock":
-            res = [res[0], float(out["dissipation_time"][0])] + res[1:]
+            res = [res[0], tdiss] + res[1:]   # model.py:643
         return res
     nrows = int(out["stats"][0][7]) + 1  # row 0 + one row per interval (model.py:158-187 trims by Time != 0)
     nrows = min(nrows, timepoints + 1)
@@ -114,10 +127,18 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
         chem = pd.DataFrame(chem[:, 0, :], columns=lib.species)
         if rates is not None:
             rates = pd.DataFrame(rates[:, 0, :])
-    res = (physics, chem, rates, abundance_start)
+    if kind == "cshock":   # model.py:618-640: (physics, chem, rates, dissipation_time, abundanceStart, flag)
+        return (physics, chem, rates, tdiss, abundance_start, flag)
+    return (physics, chem, rates, abundance_start, flag)
+
+
+def _failed_result(kind, traj, flag):
+    """What the reference's wrappers return when the model never ran (empty trajectories, model.py:76-81,606-643)."""
+    if not traj:
+        return [flag, None] if kind == "cshock" else [flag]
     if kind == "cshock":
-        res = res + (float(out["dissipation_time"][0]),)
-    return res + (flag,)
+        return (None, None, None, None, None, flag)
+    return (None, None, None, None, flag)
 
 
 def cloud(param_dict=None, out_species=None, return_array=False, return_dataframe=False, return_rates=False,
