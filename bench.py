@@ -145,19 +145,32 @@ def cpu_sample_order(ncell):
     return np.random.default_rng(20261017).permutation(ncell)
 
 
-def run_oracle_sample(params, cores, seconds, cells=None):
+_ORACLES = {}
+
+
+def oracle_for(tag):
+    """The CPU restatement for one network (native build), cached."""
+    if tag not in _ORACLES:
+        from oracle.oracle import Oracle
+        from uclchem_b200.network import Network, load_default
+        net = load_default() if tag == "default" else Network.from_json(ROOT / "uclchem_b200" / "networks" / f"{tag}.json")
+        _ORACLES[tag] = Oracle(net, native=True)
+    return _ORACLES[tag]
+
+
+def run_oracle_sample(params, cores, seconds, cells=None, kind=0, y0=None, tag="default"):
     """Time the CPU restatement on the workload: one work queue over `cores` threads (every core stays busy until
     the bound), cells in `cpu_sample_order`, stopped `seconds` after the start.  A model still running at the
     bound stops (oracle guard, flag -98) and is left out of numerator and denominator -- which favours the CPU
     figure, because the cells that get cut are the slow ones.  Returns a dict."""
     from oracle.oracle import Oracle
-    from uclchem_b200.network import load_default
     order = cpu_sample_order(params.shape[1]) if cells is None else np.asarray(cells)
     order = order[: max(cores, int(cores * seconds / 1.5))]   # more than the queue can finish (>= 1.5 s per model)
-    orc = Oracle(load_default(), native=True)
+    orc = oracle_for(tag)
     orc.set_deadline(seconds)
     t0 = time.perf_counter()
-    y, _, flag, st, secs = orc.run_grid(0, np.ascontiguousarray(params[:, order]), nthreads=cores, timed=True)
+    y, _, flag, st, secs = orc.run_grid(kind, np.ascontiguousarray(params[:, order]), y0=None if y0 is None else y0[order],
+                                        nthreads=cores, timed=True)
     wall = time.perf_counter() - t0
     orc.set_deadline(0.0)
     fin = (flag != Oracle.FLAG_DEADLINE) & (secs >= 0)
@@ -198,11 +211,10 @@ def assemble_line(*, a, world, n_ok, n_cells, n_budget, workload, wall_s, kernel
     w_flop = (S["nfe"] * f_rhs + S["nje"] * f_jac + S["nlu"] * f_lu + S["nni"] * f_solve + S["nintervals"] * f_rates)
     w_exec = (S["nfe"] * f_rhs + S["nje"] * f_jac + S["nlu"] * f_lu_exec + S["nni"] * f_solve_exec + S["nintervals"] * f_rates)
     kern_s = kernel_ms / 1e3
-    # rank 0's counters cover n_stat cells of n_cells / world per rank: same work per rank by construction
-    scale = (n_cells / world) / n_stat
-    tfl = w_flop * scale / kern_s / 1e12
+    # `stats` holds every cell rank 0 launched in the timed steps (all stages); kernel time is the max over ranks
+    tfl = w_flop / kern_s / 1e12
     hbm_peak, how = peak_hbm()
-    gbs = b_cell * (n_cells / world) / kern_s / 1e9
+    gbs = b_cell * n_stat / kern_s / 1e9
     roof = {"bound": "fp64", "achieved": tfl, "peak": fp64_peak_tflops, "unit": "TFLOP/s",
             "frac": tfl / fp64_peak_tflops if fp64_peak_tflops else None, "traffic": traffic,
             "peak_source": "DFMA micro-benchmark run by this process (uclgpu_fp64_peak); MEASURED_PEAKS.json has no fp64 figure",
@@ -233,37 +245,168 @@ def assemble_line(*, a, world, n_ok, n_cells, n_budget, workload, wall_s, kernel
     }
 
 
+
+# ------------------------------------------------------------------------------------------------ workloads
+class StepSpec:
+    """Inputs of one step: `params` [NPARAM, n] of the models that are counted, optionally preceded by a first
+    stage (`stage1` = (kind, params)) whose final abundances are the starting states: cell c starts from
+    stage-1 row y0_index[c]."""
+
+    def __init__(self, kind, params, stage1=None, y0_index=None):
+        self.kind, self.params, self.stage1, self.y0_index = kind, np.ascontiguousarray(params), stage1, y0_index
+
+
+class Workload:
+    tag = "default"
+    nslice = NSLICE
+    disjoint_ranks = True     # ranks take different steps of one grid (False: every rank has its own grid)
+
+    def step(self, k):
+        raise NotImplementedError
+
+
+class Config1(Workload):
+    """BASELINE configs[0]: the reference's own single static cloud (n_H = 1e4, T = 10 K, 1 Myr); a step is one
+    such model per SM (148 identical models), the line also quotes the time of ONE model."""
+    nslice = 1
+
+    def __init__(self, rank, world, a):
+        from uclchem_b200.params import params_from_dict
+        self.p = params_from_dict({"initialDens": np.full(148, 1e4), "initialTemp": 10.0, "finalTime": 1.0e6,
+                                   "freefall": False, "endAtFinalDensity": False})
+        self.desc = {"workload": "config[0]: single static cloud model, n_H = 1e4, T = 10 K, 1 Myr, default network",
+                     "step": "148 identical models, one per SM (a model is one sequential chain: its wall time is the step time)",
+                     "cells_per_gpu_per_step": 148}
+
+    def step(self, k):
+        return StepSpec(0, self.p)
+
+
+class Config2(Workload):
+    disjoint_ranks = False
+
+    def __init__(self, rank, world, a):
+        self.params = config2_params(rank=rank, world=world)
+        if a.cells:
+            self.params = np.ascontiguousarray(self.params[:, np.linspace(0, self.params.shape[1] - 1, a.cells).astype(int)])
+        n = self.params.shape[1]
+        self.slices = [slice_cells(n, q) for q in range(NSLICE)]
+        self.desc = {"workload": "config[1]: 10^4-point static cloud grid (25 n_H x 20 T x 20 zeta), 1 Myr, default network "
+                                 "335 species / 3203 reactions, reltol 1e-8, ALL cells"
+                                 + (f"; {world} ranks: zeta axis refined to {20 * world} points, one 10^4-cell grid per GPU" if world > 1 else ""),
+                     "step": f"one interleaved quarter of the rank's grid ({len(self.slices[0])} cells per GPU, flat index = step mod {NSLICE}); "
+                             f"{NSLICE} consecutive steps cover the grid once",
+                     "cells_per_gpu_per_step": int(len(self.slices[0])), "cells_total": int(world * n)}
+
+    def step(self, k):
+        return StepSpec(0, self.params[:, self.slices[k % NSLICE]])
+
+
+class Config3(Workload):
+    """BASELINE configs[2]: stage 1 free-fall clouds 1e2 -> n_f for 40 n_f x 25 zeta (1 000 runs),
+    stage 2 hot_core(temp_indx 1..5, max_temperature 100..400 K in 20 steps) from each: 100 000 models.  A step
+    takes 8 of the 1 000 (n_f, zeta) pairs (a fixed shuffle) with all 100 hot cores of each: 8 stage-1 models,
+    then 800 hot cores whose starting states are read from the stage-1 result table by index."""
+    nslice = 125
+
+    def __init__(self, rank, world, a):
+        nf, ze = np.meshgrid(10 ** np.linspace(4, 7, 40), 10 ** np.linspace(0, 2, 25), indexing="ij")
+        self.pairs = np.stack([nf.ravel(), ze.ravel()], axis=1)[np.random.default_rng(3).permutation(1000)]
+        ti, mt = np.meshgrid(np.arange(1, 6), np.linspace(100, 400, 20), indexing="ij")
+        self.ti, self.mt = ti.ravel().astype(float), mt.ravel()
+        self.desc = {"workload": "config[2]: two-stage grid, 1 000 free-fall clouds (40 n_f x 25 zeta, 1e2 -> n_f) each feeding 100 "
+                                 "hot cores (5 temp_indx x 20 max_temperature, freezeFactor 0, 1 Myr): 100 000 models",
+                     "step": "8 (n_f, zeta) pairs of a fixed shuffle: 8 stage-1 models, then their 800 hot cores starting from the "
+                             "stage-1 result table (uclgpu_opts.y0_index); 125 steps cover the grid; counted models = hot cores",
+                     "cells_per_gpu_per_step": 800, "cells_total": 100000}
+
+    def step(self, k):
+        from uclchem_b200.params import params_from_dict
+        pr = self.pairs[(k % self.nslice) * 8:(k % self.nslice) * 8 + 8]
+        s1 = params_from_dict({"freefall": True, "endAtFinalDensity": True, "initialDens": 1e2, "finalDens": pr[:, 0],
+                               "zeta": pr[:, 1], "initialTemp": 10.0, "finalTime": 1.0e7})
+        idx = np.repeat(np.arange(8), 100)
+        s2 = params_from_dict({"initialDens": pr[idx, 0], "zeta": pr[idx, 1], "initialTemp": 10.0, "finalTime": 1.0e6,
+                               "freezeFactor": 0.0, "freefall": False, "endAtFinalDensity": False,
+                               "temp_indx": np.tile(self.ti, 8), "max_temperature": np.tile(self.mt, 8)})
+        return StepSpec(1, s2, stage1=(0, s1), y0_index=idx.astype(np.int32))
+
+
+class Config4(Workload):
+    """BASELINE configs[3]: 10^4 C-shocks, 100 velocities (10..45 km/s) x 100 pre-shock densities (10^3.5..10^6),
+    pre-shock abundances from a free-fall collapse to each density, tolerances of notebooks/3_running_a_grid.py."""
+    nslice = 10
+
+    def __init__(self, rank, world, a):
+        self.vs = np.linspace(10, 45, 100)
+        self.n0 = 10 ** np.linspace(3.5, 6, 100)
+        self.desc = {"workload": "config[3]: C-shock grid, 100 shock velocities (10-45 km/s) x 100 pre-shock densities (10^3.5-10^6), "
+                                 "timestep_factor 0.01, finalTime 1e5 yr, reltol 1e-6, abstol_min 1e-20, pre-shock abundances from a "
+                                 "free-fall collapse 1e2 -> n0",
+                     "step": "10 densities (every tenth) x 100 velocities: 10 stage-1 free-fall models, then 1 000 shocks; 10 steps cover the grid",
+                     "cells_per_gpu_per_step": 1000, "cells_total": 10000}
+
+    def step(self, k):
+        from uclchem_b200.params import params_from_dict
+        n0 = self.n0[(k % 10)::10]
+        s1 = params_from_dict({"freefall": True, "endAtFinalDensity": True, "initialDens": 1e2, "finalDens": n0,
+                               "initialTemp": 10.0, "finalTime": 1.0e7})
+        idx = np.repeat(np.arange(10), 100)
+        s2 = params_from_dict({"initialDens": n0[idx], "initialTemp": 10.0, "finalTime": 1.0e5, "shock_vel": np.tile(self.vs, 10),
+                               "timestep_factor": 0.01, "minimum_temperature": 0.0, "reltol": 1e-6, "abstol_min": 1e-20})
+        return StepSpec(2, s2, stage1=(0, s1), y0_index=idx.astype(np.int32))
+
+
+class Config5(Workload):
+    """BASELINE configs[4]: 10^6 static clouds (100^3 over the config-2 ranges) on the network MakeRates generates
+    with add_crp_photo_to_grain (335 species / 3453 reactions), tolerances of tests/test_photo_on_grain.py."""
+    tag = "crp_photo"
+    nslice = 400
+
+    def __init__(self, rank, world, a):
+        self.axes = (10 ** np.linspace(3, 7, 100), np.linspace(10, 100, 100), 10 ** np.linspace(0, 3, 100))
+        self.desc = {"workload": "config[4]: 10^6-point static cloud grid (100 n_H x 100 T x 100 zeta over the config-2 ranges), 1 Myr, "
+                                 "crp-photo network 335 species / 3453 reactions, reltol 1e-5, abstol_min 1e-15",
+                     "step": "every 400th cell of the grid (2 500 cells per GPU); 400 steps cover the grid",
+                     "cells_per_gpu_per_step": 2500, "cells_total": 1000000}
+
+    def step(self, k):
+        from uclchem_b200.params import params_from_dict
+        i = np.arange(k % 400, 1000000, 400)
+        d, t, z = np.unravel_index(i, (100, 100, 100))
+        return StepSpec(0, params_from_dict({"initialDens": self.axes[0][d], "initialTemp": self.axes[1][t], "zeta": self.axes[2][z],
+                                             "radfield": 1.0, "baseAv": 2.0, "rout": 0.05, "finalTime": 1.0e6, "freefall": False,
+                                             "endAtFinalDensity": False, "reltol": 1e-5, "abstol_min": 1e-15}))
+
+
+WORKLOADS = {1: Config1, 2: Config2, 3: Config3, 4: Config4, 5: Config5}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=NSLICE)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", type=int, default=2, choices=sorted(WORKLOADS),
+                    help="BASELINE.json configs[workload-1]; 2 (the 10^4 static-cloud grid) is the headline and the default")
     ap.add_argument("--step-budget", type=int, default=STEP_BUDGET,
                     help="BDF steps after which a cell is abandoned (flag -5, not counted); 0 = the reference's unbounded crawl")
-    ap.add_argument("--transfer-band", type=float, default=0.0,
-                    help="opt-in deviation uclgpu_opts.transfer_band (DESIGN.md section 6); 0 = reference behaviour")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="bound of the cpu_baseline sample")
     ap.add_argument("--cells", type=int, default=0, help="debug: override the grid size (not a valid bench line)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    params = config2_params(rank=rank, world=world)
-    if a.cells:
-        params = np.ascontiguousarray(params[:, np.linspace(0, params.shape[1] - 1, a.cells).astype(int)])
-    ncell = params.shape[1]
-    slices = [slice_cells(ncell, q) for q in range(NSLICE)]
-    workload = {"workload": f"config[1]: 10^4-point static cloud grid (25 n_H x 20 T x 20 zeta), 1 Myr, default network "
-                            "335 species / 3203 reactions, reltol 1e-8, ALL cells"
-                            + (f"; {world} ranks: zeta axis refined to {20 * world} points, one 10^4-cell grid per GPU" if world > 1 else ""),
-                "step": f"one interleaved quarter of the rank's grid ({len(slices[0])} cells per GPU, flat index = step mod {NSLICE}); "
-                        f"{NSLICE} consecutive steps cover the grid once",
-                "cells_per_gpu_per_step": int(len(slices[0])), "cells_total": int(world * ncell),
-                "step_budget": a.step_budget, "transfer_band": a.transfer_band,
-                "timing": "L2 flushed (256 MiB write) between timed steps; inputs (5 MB per step) are far smaller than L2 "
-                          "but are read once per cell",
-                "warmup_step": "one pass over a 296-cell stride of the same grid (same kernel and launch shape), step budget 20 000"}
+    wl = WORKLOADS[a.workload](rank, world, a)
+    workload = dict(wl.desc)
+    workload.update({"step_budget": a.step_budget,
+                     "timing": "L2 flushed (256 MiB write) between timed steps; a step's inputs are read once per cell",
+                     "warmup_step": "one pass over a 296-cell stride of the first step's cells (same kernel and launch shape), "
+                                    "step budget 20 000"})
+
+    def step_id(k):   # ranks share one grid: consecutive steps are dealt round-robin; own grid per rank: same step index
+        return k * world + rank if wl.disjoint_ranks else k
 
     # ------------------------------------------------------------------ reference arm (CPU restatement)
     if a.impl == "reference":
@@ -271,13 +414,18 @@ def main():
             return
         cores = cpu_cores()
         seconds = float(min(200.0, max(60.0, 30.0 * a.steps)))   # one continuous sample, reported per step
+        spec = wl.step(0)
+        y0 = None
+        if spec.stage1 is not None:   # starting states of the sampled cells: the CPU runs their first stage itself
+            log("reference arm: first stage on the CPU")
+            y0 = oracle_for(wl.tag).run_grid(spec.stage1[0], spec.stage1[1], nthreads=cores)[0][spec.y0_index]
         if a.warmup:
             log(f"reference arm: warm-up sample ({min(5.0, a.warmup * 1.0):.0f} s) on {cores} cores")
-            run_oracle_sample(params, cores, min(5.0, a.warmup * 1.0))
+            run_oracle_sample(spec.params, cores, min(5.0, a.warmup * 1.0), kind=spec.kind, y0=y0, tag=wl.tag)
         log(f"reference arm: {seconds:.0f} s sample on {cores} cores")
-        r = run_oracle_sample(params, cores, seconds)
+        r = run_oracle_sample(spec.params, cores, seconds, kind=spec.kind, y0=y0, tag=wl.tag)
         cpu = cpu_baseline_dict(r, cores, seconds)
-        workload["step"] = (f"one continuous {seconds:.0f} s sample of the same grid (shuffled work queue, all cores busy), "
+        workload["step"] = (f"one continuous {seconds:.0f} s sample of the first step's cells (shuffled work queue, all cores busy), "
                             f"reported as {a.steps} equal steps")
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
@@ -290,33 +438,39 @@ def main():
     import torch
     import torch.distributed as dist
     from uclchem_b200._capi import STAT_FIELDS, UclgpuOpts, UclgpuStats, get_library
+    from uclchem_b200.sharding import gather_rows, max_over_ranks
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    lib = get_library("default")          # raises if the CUDA extension is missing: no fallback
+    lib = get_library(wl.tag)          # raises if the CUDA extension is missing: no fallback
     lib.init([local_rank])
     neq = lib.neq
     nstat = len(STAT_FIELDS)
     pd_, pi_ = C.POINTER(C.c_double), C.POINTER(C.c_int32)
 
     class Batch:
-        """Pinned host buffers of one step's cells (what a caller of uclgpu_run_grid owns)."""
+        """Pinned host buffers of one call of uclgpu_run_grid (what a caller of the C ABI owns)."""
 
-        def __init__(self, p):
-            self.n = p.shape[1]
+        def __init__(self, kind, p, y0_index=None):
+            self.kind, self.n = kind, p.shape[1]
             self.params = torch.from_numpy(np.ascontiguousarray(p)).pin_memory()
             self.y = torch.zeros((self.n, neq), dtype=torch.float64).pin_memory()
             self.phys = torch.zeros((self.n, 8), dtype=torch.float64).pin_memory()
             self.flag = torch.zeros(self.n, dtype=torch.int32).pin_memory()
             self.stats = torch.zeros((self.n, nstat), dtype=torch.int64).pin_memory()
+            self.y0_index = None if y0_index is None else torch.from_numpy(np.ascontiguousarray(y0_index, np.int32)).pin_memory()
 
-        def run(self, budget):
+        def run(self, budget, y0_table=None):
             opts = UclgpuOpts()
             opts.step_budget = budget
-            opts.transfer_band = a.transfer_band
-            rc = lib.lib.uclgpu_run_grid(0, self.n, C.cast(self.params.data_ptr(), pd_), None,
+            y0p = None
+            if y0_table is not None:
+                opts.y0_index = C.cast(self.y0_index.data_ptr(), pi_)
+                opts.ny0 = y0_table.shape[0]
+                y0p = C.cast(y0_table.data_ptr(), pd_)
+            rc = lib.lib.uclgpu_run_grid(self.kind, self.n, C.cast(self.params.data_ptr(), pd_), y0p,
                                          C.cast(self.y.data_ptr(), pd_), C.cast(self.phys.data_ptr(), pd_),
                                          C.cast(self.flag.data_ptr(), pi_),
                                          C.cast(self.stats.data_ptr(), C.POINTER(UclgpuStats)), C.byref(opts))
@@ -324,15 +478,50 @@ def main():
             return lib.last_kernel_ms(local_rank)
 
         def h2d_bytes(self):
-            return self.params.numel() * 8
+            return self.params.numel() * 8 + (0 if self.y0_index is None else self.y0_index.numel() * 4)
 
         def d2h_bytes(self):
             return self.y.numel() * 8 + self.phys.numel() * 8 + self.flag.numel() * 4 + self.stats.numel() * 8
 
-    batches = [Batch(params[:, s]) for s in slices]
-    warm = Batch(params[:, np.linspace(0, ncell - 1, min(ncell, 296)).astype(int)])
+    class Step:
+        """One step: an optional first stage, then the counted models (which start from the first stage's table)."""
+
+        def __init__(self, spec):
+            self.spec = spec
+            self.s1 = Batch(spec.stage1[0], spec.stage1[1]) if spec.stage1 is not None else None
+            self.main = Batch(spec.kind, spec.params, spec.y0_index)
+            self.n = self.main.n
+
+        def run(self, budget):
+            ms = nl = 0.0
+            if self.s1 is not None:
+                m1, n1 = self.s1.run(budget)
+                ms, nl = ms + m1, nl + n1
+            m2, n2 = self.main.run(budget, None if self.s1 is None else self.s1.y)
+            return ms + m2, int(nl + n2)
+
+        def all_stats(self):
+            parts = [self.main.stats.numpy().copy()] + ([self.s1.stats.numpy().copy()] if self.s1 is not None else [])
+            return np.concatenate(parts)
+
+        def h2d_bytes(self):
+            return self.main.h2d_bytes() + (0 if self.s1 is None else self.s1.h2d_bytes() + self.s1.y.numel() * 8)
+
+        def d2h_bytes(self):
+            return self.main.d2h_bytes() + (0 if self.s1 is None else self.s1.d2h_bytes())
+
+    n_distinct = min(a.steps, wl.nslice if not wl.disjoint_ranks else a.steps)
+    steps = {}
+    for k in range(a.steps):
+        sid = step_id(k) % wl.nslice
+        if sid not in steps:
+            steps[sid] = Step(wl.step(sid))
+    first = steps[step_id(0) % wl.nslice]
+    wsel = np.linspace(0, first.n - 1, min(first.n, 296)).astype(int)
+    wspec = first.spec
+    warm = Step(StepSpec(wspec.kind, wspec.params[:, wsel], wspec.stage1, None if wspec.y0_index is None else wspec.y0_index[wsel]))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    n_max = max(b.n for b in batches)
+    n_max = max(st_.n for st_ in steps.values())
     stage = torch.empty((n_max, neq + 1), dtype=torch.float64, device=dev)       # y_final + flag, for the gather
     gathered = [torch.empty_like(stage) for _ in range(world)] if (world > 1 and rank == 0) else None
     h_gathered = torch.empty((world, n_max, neq + 1), dtype=torch.float64).pin_memory() if (world > 1 and rank == 0) else None
@@ -345,7 +534,7 @@ def main():
     for _ in range(a.warmup):
         warm.run(20000)
         flush.fill_(1)
-    log(f"warm-up done ({a.warmup} x {warm.n} cells); timing {a.steps} steps of {batches[0].n} cells")
+    log(f"warm-up done ({a.warmup} x {warm.n} cells); timing {a.steps} steps of {first.n} cells")
 
     kernel_ms, launches = 0.0, 0
     n_ok = n_budget = n_cells = 0
@@ -354,29 +543,28 @@ def main():
         barrier()
         t0 = time.perf_counter()
         for k in range(a.steps):
-            b = batches[k % NSLICE]
+            b = steps[step_id(k) % wl.nslice]
             ms, nl = b.run(a.step_budget)
             kernel_ms += ms
             launches += nl
             if world > 1:
                 # the only collective of the path: every model's final abundances and flag go to rank 0
-                stage[: b.n, :neq].copy_(b.y, non_blocking=True)
-                stage[: b.n, neq].copy_(b.flag.to(torch.float64), non_blocking=True)
-                dist.gather(stage, gathered, dst=0)
+                stage[: b.n, :neq].copy_(b.main.y, non_blocking=True)
+                stage[: b.n, neq].copy_(b.main.flag.to(torch.float64), non_blocking=True)
+                gather_rows(stage, rank, world, out=gathered)
                 if rank == 0:
                     for r_ in range(world):
                         h_gathered[r_].copy_(gathered[r_], non_blocking=True)
                     torch.cuda.synchronize()
-            fl = b.flag.numpy()
+            fl = b.main.flag.numpy()
             n_ok += int((fl == 0).sum())
             n_budget += int((fl == -5).sum())
             n_cells += b.n
-            step_stats.append(b.stats.numpy().copy())
+            step_stats.append(b.all_stats())
             flush.fill_(1)  # L2 flush between timed iterations
         barrier()
         wall = time.perf_counter() - t0
     clocks = clk.summary()
-    t = torch.tensor([wall, kernel_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([n_ok, n_budget, n_cells, launches], dtype=torch.float64, device=dev)
     per_rank = [kernel_ms / a.steps]
     if world > 1:
@@ -384,9 +572,8 @@ def main():
         allk = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allk, mine)
         per_rank = [float(x.item()) for x in allk]
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    wall, kernel_ms = t[0].item(), t[1].item()
+    wall, kernel_ms = max_over_ranks([wall, kernel_ms], world, dev)
     n_ok, n_budget, n_cells, launches = (int(x) for x in cnt.tolist())
     log(f"rank {rank}: {a.steps} steps in {wall:.1f} s, kernel {kernel_ms / 1e3:.1f} s")
 
@@ -396,27 +583,23 @@ def main():
         lib.lib.uclgpu_work_model(flop)
         pk = C.c_double(0.0)
         lib.lib.uclgpu_fp64_peak(local_rank, C.byref(pk))
-        traffic = None   # DRAM bytes of one k_integrate launch of this workload, from the committed ncu launch list
+        traffic = None   # DRAM bytes of one k_integrate launch of the default workload, from the committed ncu launch list
         tf = ROOT / "profiles" / "traffic.json"
-        if tf.exists() and not a.cells:
+        if tf.exists() and not a.cells and a.workload == 2:
             traffic = json.loads(tf.read_text()).get("k_integrate_dram_bytes_per_step_launch")
         cores = cpu_cores()
         cpu, parity = None, {"gpu_flags_nonzero": int(n_cells - n_ok)}
         if world == 1:
-            # cpu_baseline on the cells the timed steps processed; the finished ones double as the parity sample
-            done = np.concatenate([slices[k % NSLICE] for k in range(min(a.steps, NSLICE))])
-            order = cpu_sample_order(ncell)
-            order = order[np.isin(order, done)]
+            # cpu_baseline on cells the timed steps processed (the first step's); the finished ones double as the
+            # parity sample.  Staged workloads: the sampled cells start from the GPU's own first-stage results.
+            b = first
             log(f"cpu_baseline: oracle work queue on {cores} cores, bounded at {a.cpu_seconds:.0f} s")
             try:
-                r = run_oracle_sample(params, cores, a.cpu_seconds, cells=order)
+                y0 = None if b.s1 is None else b.s1.y.numpy()[b.spec.y0_index]
+                r = run_oracle_sample(b.spec.params, cores, a.cpu_seconds, kind=b.spec.kind, y0=y0, tag=wl.tag)
                 cpu = cpu_baseline_dict(r, cores, a.cpu_seconds)
-                y_gpu = np.zeros((ncell, neq))
-                f_gpu = np.full(ncell, -99, np.int32)
-                for q in range(min(a.steps, NSLICE)):
-                    y_gpu[slices[q]] = batches[q].y.numpy()
-                    f_gpu[slices[q]] = batches[q].flag.numpy()
                 cells = r["cells"]
+                f_gpu, y_gpu = b.main.flag.numpy(), b.main.y.numpy()
                 ok = r["finished"] & (r["flag"] == 0) & (f_gpu[cells] == 0)
                 yr, yg = r["y"][ok][:, :335], y_gpu[cells[ok]][:, :335]
                 m = yr > 1e-15
@@ -433,9 +616,11 @@ def main():
         line = assemble_line(a=a, world=world, n_ok=n_ok, n_cells=n_cells, n_budget=n_budget, workload=workload,
                              wall_s=wall, kernel_ms=kernel_ms, launches=launches, stats=np.concatenate(step_stats),
                              clocks=clocks, work_model=list(flop), fp64_peak_tflops=pk.value,
-                             h2d_bytes=batches[0].h2d_bytes(), d2h_bytes=batches[0].d2h_bytes(), cpu=cpu, parity=parity,
+                             h2d_bytes=first.h2d_bytes(), d2h_bytes=first.d2h_bytes(), cpu=cpu, parity=parity,
                              traffic=traffic, stat_fields=STAT_FIELDS, per_rank_kernel_ms=per_rank,
                              gather_bytes=(world - 1) * n_max * (neq + 1) * 8 if world > 1 else 0)
+        if a.workload == 1:
+            line["single_model_seconds"] = kernel_ms / 1e3 / a.steps
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

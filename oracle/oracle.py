@@ -55,7 +55,7 @@ class OrcStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("nst", "nfe", "nje", "nlu", "nni", "ncfn", "netf", "nintervals")]
 
 
-_SRCS = ("orc_vode.c", "orc_chem.c", "orc_model.c", "orc_cshock.c", "orc_vode.h", "orc_internal.h", "uclchem_oracle.h")
+_SRCS = ("orc_vode.c", "orc_chem.c", "orc_model.c", "orc_cshock.c", "orc_collapse.c", "orc_vode.h", "orc_internal.h", "uclchem_oracle.h")
 
 
 def build(force: bool = False) -> Path:

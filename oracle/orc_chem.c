@@ -657,9 +657,6 @@ void orc_init_desfrac(orc_model *m)
     }
 }
 
-static double g_transfer_band = 0.0;
-void orc_set_transfer_band(double band) { g_transfer_band = band; }
-
 /* GETYDOT, odes.f90:6-5181, as a walk over the MakeRates rules */
 void orc_getydot(const orc_network *net, const double *rate, const double *y, double blr,
                  double surface_coverage, double safe_mantle, double safe_bulk, double dens, double *ydot,
@@ -706,24 +703,6 @@ void orc_getydot(const orc_network *net, const double *rate, const double *y, do
     if (surfgrowth_uncorrected) *surfgrowth_uncorrected = ss;
     /* three-phase transfer, odes.f90:4815-5153 (species order: surface block, then bulk block) */
     int nrefr = net->n_refractory;
-    if (g_transfer_band > 0.0) {
-        /* EXPERIMENT (not reference behaviour; off unless orc_set_transfer_band was called): the two branches
-         * of the transfer are blended with a C1 weight while the net surface growth S is smaller than
-         * band * sum_s |ydot_s|, i.e. while S is a small difference of the surface species' own rates. */
-        double S = ydot[iS], G = 0.0;
-        for (int k = 0; k < net->nsurf; k++) G += fabs(ydot[net->surface_list[k]]);
-        double eps = g_transfer_band * G, w;
-        if (S >= eps) w = 1.0;
-        else if (S <= -eps) w = 0.0;
-        else { double t = (S + eps) / (2.0 * eps); w = t * t * (3.0 - 2.0 * t); }
-        double covs = fmin(1.0, safe_bulk / safe_mantle);
-        for (int k = 0; k < net->nsurf; k++) {
-            int sI = net->surface_list[k], bI = net->bulk_list[k];
-            double c = S * ((1.0 - w) * covs * y[bI] / safe_bulk + w * surface_coverage * y[sI]);
-            ydot[sI] -= c;
-            ydot[bI] += c;
-        }
-    } else
     if (ydot[iS] < 0) {
         surface_coverage = fmin(1.0, safe_bulk / safe_mantle);
         for (int k = 0; k < net->nsurf; k++) {

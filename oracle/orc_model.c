@@ -112,6 +112,8 @@ static int model_initialize_physics(orc_model *m)
         return 0;
     case UCLGPU_CSHOCK:
         return orc_cshock_initialize(m);
+    case UCLGPU_COLLAPSE:
+        return orc_collapse_initialize(m);
     }
     return -1;
 }
@@ -151,6 +153,9 @@ static void update_target_time(orc_model *m)
     case UCLGPU_CSHOCK:
         orc_cshock_update_target_time(m);
         break;
+    case UCLGPU_COLLAPSE:
+        orc_collapse_update_target_time(m);
+        break;
     }
 }
 
@@ -173,6 +178,9 @@ static void model_update_physics(orc_model *m)
         break;
     case UCLGPU_CSHOCK:
         orc_cshock_update_physics(m);
+        break;
+    case UCLGPU_COLLAPSE:
+        orc_collapse_update_physics(m);
         break;
     }
 }

@@ -154,3 +154,40 @@ def test_cshock_return_conventions_host_logic(oracle, net, monkeypatch):
     assert model.cshock(20.0, param_dict={"nonsense": 1.0}, return_array=True)[-1] == -1
     with pytest.raises(KeyError):
         model.cloud_grid({"initialDensity": [1e3, 1e4]})
+
+
+def test_collapse_model_host_logic_and_oracle_physics(oracle, net, monkeypatch):
+    """uclchem.model.collapse mirror (model.py:319-426) through the oracle-backed library double, and the oracle's
+    collapse physics (oracle/orc_collapse.c) against an independent numpy evaluation of the filament fits of
+    collapse.f90:178-266: parcel density rho(rout, t) and Av = baseAv + N(rin..rout) / 1.6e21."""
+    from uclchem_b200 import model
+    monkeypatch.setattr(model, "get_library", lambda *a, **k: _OracleBackedLibrary(oracle, net))
+    with pytest.raises(ValueError, match="collapse must be one of"):
+        model.collapse("spherical", None)
+    with pytest.raises(NotImplementedError):
+        model.collapse("filament", "physics.dat")
+    pd_ = {"rout": 0.2, "baseAv": 1.0, "finalTime": 2.0e3, "initialTemp": 10.0}
+    phys, chem, rates, start, flag = model.collapse("filament", None, param_dict=pd_, return_array=True)
+    assert flag == 0 and rates is None and phys.shape[1:] == (1, 8) and chem.shape[2] == net.nspec
+    t = phys[:, 0, 0]
+    assert t[0] == 0.0 and t[-1] >= 2.0e3 and np.allclose(t[2:] / t[1:-1], 10.0)          # cadence collapse.f90:63-75 below 1e3 yr
+    f32 = lambda x: float(np.float32(x))
+    mh, pi, pc, spy = 1.67262164e-24, f32(3.141592654), 3.086e18, 3.16e7
+    unitt = (2 * pi * 6.67e-8 * 2.2e4 * mh) ** -0.5 / spy
+    unitr = np.sqrt(1.38e-16 * 10 / 2 / mh) * (2 * pi * 6.67e-8 * 2.2e4 * mh) ** -0.5 / pc
+    def profile(r, tt):
+        tn = tt / unitt
+        rho0 = 10 ** (f32(3.54) * (f32(5.47) - tn) ** f32(-0.15) - f32(2.73))
+        r0 = 10 ** (f32(-1.34) * (f32(5.47) - tn) ** f32(-0.15) + f32(1.47))
+        a = 2.0 - 0.5 * (tn / f32(5.47)) ** 9
+        return 2.2e4 * rho0 / (1 + (r / unitr / r0) ** 2) ** a
+    for row in (1, 5, len(t) - 1):
+        assert phys[row, 0, 1] == pytest.approx(profile(0.2, t[row]), rel=1e-12)         # velocity term: dt = 0 (reference quirk)
+        r = np.linspace(0.0, 0.2, 10001)
+        rho = profile(r, t[row])
+        coldens = np.sum(0.5 * (rho[1:] + rho[:-1]) * (0.2 / 10000) * pc)
+        assert phys[row, 0, 4] == pytest.approx(1.0 + coldens / 1.6e21, rel=1e-10)
+    # Bonnor-Ebert modes run to 0.97 of the fit's time span whatever finalTime says (collapse.f90:36-41);
+    # an unknown mode is a physics initialisation error (flag -2), never an exception
+    from uclchem_b200.params import params_from_dict
+    assert oracle.run_model(3, params_from_dict({"collapse_mode": 7})[:, 0])["flag"] == -2

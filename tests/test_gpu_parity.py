@@ -287,3 +287,25 @@ def test_config2_cells_at_1myr_against_oracle_fixture(lib):
     assert (out["flag"] == 0).all(), dict(zip(cells.tolist(), out["flag"].tolist()))
     worst = {int(c): max_dex(out["y_final"][k, :335], fx["y_final"][k, :335]) for k, c in enumerate(cells)}
     assert max(worst.values()) <= DEX_TOL, worst
+
+
+def test_collapse_model_against_oracle(lib, oracle):
+    """collapse.f90 (north-star `collapse`; no golden exists: parity pinned only via the self-validated oracle).
+    BE4 at full length (0.97 x 1.855e5 yr, 184 output intervals: Bonnor-Ebert profile, enclosed-mass radius search),
+    filament and ambipolar over their first 2e4 yr, plus the reference's refusal of an unknown mode."""
+    p = params_from_dict({"collapse_mode": [2, 3, 4, 9], "rout": [0.2, 0.2, 0.5, 0.2], "baseAv": 1.0, "initialTemp": 10.0,
+                          "finalTime": 2.0e4})
+    out = lib.run_grid(3, p, timepoints=400, want_physics=True, want_chem=True)
+    assert list(out["flag"]) == [0, 0, 0, -2]
+    for c in range(3):
+        r = oracle.run_model(3, p[:, c], timepoints=400)
+        n = r["physics"].shape[0]
+        assert r["flag"] == 0 and out["stats"][c][7] == r["stats"]["nintervals"] == n - 1
+        np.testing.assert_allclose(out["physics"][c, :n, 0], r["physics"][:, 0], rtol=1e-12)          # output times
+        np.testing.assert_allclose(out["physics"][c, :n, [1, 4]], r["physics"][:, [1, 4]].T, rtol=1e-9)  # density, Av
+        assert max_dex(out["y_final"][c, :335], r["y_final"][:335]) < DEX_TOL, c
+        worst = max(max_dex(out["abund"][c, row], r["abund"][row]) for row in range(1, n))
+        assert worst < DEX_TOL, (c, worst)
+    assert out["phys_final"][0, 0] > 0.97 * 1.855e5 - 1.0       # BE4 ignores finalTime (collapse.f90:39-41)
+    res = model.collapse("BE4", None, param_dict={"rout": 0.2, "baseAv": 1.0}, out_species=["CO"])
+    assert res[0] == 0 and res[1] == pytest.approx(out["y_final"][0, 49], rel=1e-12)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from uclchem_b200.sharding import gather_results, shard_range
+from uclchem_b200.sharding import gather_results, gather_rows, max_over_ranks, shard_range
 
 
 def test_shard_range_partitions_exactly():
@@ -49,3 +49,47 @@ def test_two_rank_gather_gloo():
     for p in procs:
         p.join(timeout=60)
     assert full.shape == (n, 3) and np.array_equal(full[:, 0], np.arange(n)) and mx == 6.0
+
+
+def _bench_worker(rank, world, port, q):
+    """What bench.py does per rank for N > 1, with the integration replaced by a function of the parameters."""
+    import bench
+    from uclchem_b200.params import PARAM_INDEX
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p = bench.config2_params(rank=rank, world=world)
+    sl = bench.slice_cells(p.shape[1], 1)
+    stage = torch.zeros((len(sl), 3), dtype=torch.float64)
+    stage[:, 0] = torch.from_numpy(p[PARAM_INDEX["zeta"], sl])
+    stage[:, 1] = torch.from_numpy(p[PARAM_INDEX["initialdens"], sl])
+    stage[:, 2] = float(rank)
+    blocks = gather_rows(stage, rank, world)
+    wall, kern = max_over_ranks([1.0 + rank, 10.0 - rank], world)
+    if rank == 0:
+        q.put(([b.numpy() for b in blocks], wall, kern))
+    else:
+        assert blocks is None
+    dist.destroy_process_group()
+
+
+def test_two_rank_bench_gather_gloo():
+    """N = 2: the ranks own disjoint grids (every second zeta plane), rank 0 receives every rank's rows in rank
+    order, and the timing figures are the slowest rank's."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bench_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    blocks, wall, kern = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+    assert len(blocks) == 2 and blocks[0].shape == blocks[1].shape == (2500, 3)
+    assert (blocks[0][:, 2] == 0).all() and (blocks[1][:, 2] == 1).all()
+    z0, z1 = np.unique(blocks[0][:, 0]), np.unique(blocks[1][:, 0])
+    assert len(z0) == len(z1) == 5 and not set(z0) & set(z1)          # a quarter of each rank's 20 zeta planes
+    assert np.array_equal(np.unique(blocks[0][:, 1]), np.unique(blocks[1][:, 1]))
+    assert (wall, kern) == (2.0, 10.0)

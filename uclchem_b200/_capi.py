@@ -39,7 +39,8 @@ class UclgpuStats(C.Structure):
 class UclgpuOpts(C.Structure):
     _fields_ = [("timepoints", C.c_int32), ("physics_traj", _pd), ("chem_traj", _pd), ("rates_traj", _pd),
                 ("dissipation_time", _pd), ("reserved0", C.c_int32), ("step_budget", C.c_int32),
-                ("transfer_band", C.c_double), ("cost_hint", _pd), ("chunk_bytes", C.c_int64)]
+                ("cost_hint", _pd), ("y0_index", _pi), ("ny0", C.c_int64),
+                ("chunk_bytes", C.c_int64)]
 
 
 class UclgpuError(RuntimeError):
@@ -111,8 +112,8 @@ class Library:
         return out
 
     def run_grid(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 0, want_physics=False,
-                 want_chem=False, want_rates=False, step_budget: int = 0, transfer_band: float = 0.0, cost_hint=None,
-                 chunk_bytes: int = 0):
+                 want_chem=False, want_rates=False, step_budget: int = 0, cost_hint=None,
+                 chunk_bytes: int = 0, y0_index=None):
         params = np.ascontiguousarray(params, np.float64)
         assert params.ndim == 2 and params.shape[0] == NPARAM
         ncell = params.shape[1]
@@ -121,14 +122,20 @@ class Library:
         flag = np.zeros(ncell, np.int32)
         stats = (UclgpuStats * max(1, ncell))()
         y0p = None
+        opts = UclgpuOpts()
         if y0 is not None:
             y0 = np.ascontiguousarray(y0, np.float64)
-            assert y0.shape == (ncell, self.neq)
+            if y0_index is not None:      # y0 is a table of starting states shared between cells
+                y0_index = np.ascontiguousarray(y0_index, np.int32)
+                assert y0_index.shape == (ncell,) and y0.ndim == 2 and y0.shape[1] == self.neq
+                assert ncell == 0 or (0 <= y0_index.min() and y0_index.max() < y0.shape[0])
+                opts.y0_index = y0_index.ctypes.data_as(_pi)
+                opts.ny0 = y0.shape[0]
+            else:
+                assert y0.shape == (ncell, self.neq)
             y0p = y0.ctypes.data_as(_pd)
-        opts = UclgpuOpts()
         opts.timepoints = timepoints
         opts.step_budget = step_budget
-        opts.transfer_band = transfer_band
         opts.chunk_bytes = chunk_bytes
         if cost_hint is not None:
             cost_hint = np.ascontiguousarray(cost_hint, np.float64)

@@ -62,7 +62,7 @@ def compile(tag: str = "default", force: bool = False, verbose: bool = False, va
         generate(tag)   # tables are a pure function of the network and the generator
     LIBDIR.mkdir(exist_ok=True)
     out = LIBDIR / (f"libuclgpu_{tag}_{variant}.so" if variant else f"libuclgpu_{tag}.so")
-    srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_gj.cuh", CSRC / "engine_bdf.cuh",
+    srcs = [CSRC / "uclgpu.cu", CSRC / "engine_core.cuh", CSRC / "engine_la.cuh", CSRC / "engine_gj.cuh", CSRC / "engine_bdf.cuh", CSRC / "engine_collapse.cuh",
             CSRC / "engine_model.cuh", gen, _PKG.parent / "include" / "uclgpu.h"]
     if not force and out.exists() and all(out.stat().st_mtime >= s.stat().st_mtime for s in srcs):
         return out

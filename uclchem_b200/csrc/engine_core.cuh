@@ -73,14 +73,16 @@ struct Scalars {
     int lh_on, swap_off, mxstep, kind;
     long long step_budget;
     // RHS ext quantities at the last evaluated state
-    double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S, e_w, e_dw;
-    double transfer_band; // uclgpu_opts.transfer_band (0: the reference's switch)
+    double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S;
     double dflux[2]; // fluxes of the deferred photo reactions (H2 + hv, CO + hv)
     // hotcore / cshock
     double max_temp, vs, timestep_factor, min_postshock_temp;
     double cs_dlength, cs_z1, cs_z2, cs_z3, cs_v0, cs_at, cs_vn0, cs_zn0, cs_dissipation_time, cs_max_temp,
         cs_drift_vel, cs_zn, cs_vn;
     int temp_indx;
+    // collapse.f90 module state
+    int col_mode;
+    double col_max_time, col_parcel_radius, col_mass_in_radius;
     // BDF state (names follow dvode.f90)
     double tau[14], el[14], tq[6];
     double h, hu, hscal, hnew, tn, rc, prl1, rl1, eta, etamax, crate, drc, acnrm, conp, told, rtol, dsm, del,

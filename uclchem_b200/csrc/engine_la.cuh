@@ -237,50 +237,7 @@ __device__ __noinline__ void rhs_eval(Smem &s, double *ydot)
         }
     }
     // ---- three-phase transfer odes.f90:4815-5180 ------------------------------------------------
-    if (st.transfer_band > 0.0) {
-        // OPT-IN deviation (uclgpu_opts.transfer_band, DESIGN.md "stall cells"): while the net surface growth S
-        // is a small net of the gross gas <-> surface exchange G, |S| < band * G, the two branches
-        // of the transfer (S < 0: bulk composition comes up; S >= 0: surface composition is buried) are blended
-        // with a C1 weight w(S) instead of switched, which removes the kink the integrator otherwise chatters on.
-        double S = 0.0, MB = 0.0, G = 0.0, Ys = 0.0, Yb = 0.0;
-        for (int k = lane; k < NSURF; k += 32) {
-            S += ydot[net_surface_list[k]];
-            MB += ydot[net_bulk_list[k]];
-            Ys += y[net_surface_list[k]];
-            Yb += y[net_bulk_list[k]];
-        }
-        // scale of the band: the gross exchange between gas and surface (freeze-out + every desorption channel),
-        // of which S is the small net
-        {
-            const int lo[7] = {NET_FREEZE_LO, NET_THERM_LO, NET_DESOH2_LO, NET_DESCR_LO, NET_DEUVCR_LO, NET_LHDES_LO, NET_ERDES_LO};
-            const int hi[7] = {NET_FREEZE_HI, NET_THERM_HI, NET_DESOH2_HI, NET_DESCR_HI, NET_DEUVCR_HI, NET_LHDES_HI, NET_ERDES_HI};
-#pragma unroll
-            for (int t = 0; t < 7; t++)
-                for (int r = lo[t] + lane; r <= hi[t]; r += 32) G += fabs(s.flux[r]);
-        }
-        S = warp_sum(S); G = warp_sum(G); MB = warp_sum(MB); Ys = warp_sum(Ys); Yb = warp_sum(Yb);
-        const double eps = st.transfer_band * G;
-        double w, dw = 0.0;
-        if (S >= eps) w = 1.0;
-        else if (S <= -eps) w = 0.0;
-        else { const double t = (S + eps) / (2.0 * eps); w = t * t * (3.0 - 2.0 * t); dw = 6.0 * t * (1.0 - t) / (2.0 * eps); }
-        const double qs = fmin(1.0, st.e_sb / st.e_sm) / st.e_sb;
-        BLOCK_SYNC(); // every warp has read the uncorrected ydot
-        if (tid < NSURF) {
-            int si = net_surface_list[tid], bi = net_bulk_list[tid];
-            double c = S * ((1.0 - w) * qs * y[bi] + w * C_COV0 * y[si]);
-            ydot[si] -= c;
-            ydot[bi] += c;
-        } else if (tid == NSURF) {
-            double C = S * ((1.0 - w) * qs * Yb + w * C_COV0 * Ys);
-            ydot[NET_IB] = MB + C;
-            ydot[NET_IS] = S - C;
-            ydot[NET_ID] = densdot_dev(st, y[NET_ID]);
-            st.e_S = S;
-            st.e_w = w;
-            st.e_dw = dw;
-        }
-    } else {
+    {
         double S = 0.0, MB = 0.0;
         for (int k = lane; k < NSURF; k += 32) {
             S += ydot[net_surface_list[k]];
@@ -306,8 +263,6 @@ __device__ __noinline__ void rhs_eval(Smem &s, double *ydot)
             ydot[NET_IS] = S - C;
             ydot[NET_ID] = densdot_dev(st, y[NET_ID]);
             st.e_S = S;
-            st.e_w = shrink ? 0.0 : 1.0;
-            st.e_dw = 0.0;
         }
     }
     if (st.p[UCL_P_ENFORCECHARGECONSERVATION] != 0.0 && warp == NWARPS - 1) {
@@ -365,40 +320,31 @@ __device__ __noinline__ void jac_eval(Smem &s)
             val[NET_DD_POS] += ddensdot_dev(st, y[NET_ID]);
         }
         if (tid >= 128 && tid < 128 + NSURF) {
-            // c_k = S [(1-w) q_s y_b + w cov0 y_s]: w = 0 / 1 with w' = 0 is the reference's switch
             int k = tid - 128;
             const uint16_t *tp = net_tr_pos + 10 * k;
             int si = net_surface_list[k], bi = net_bulk_list[k];
-            const double w = st.e_w, dw = st.e_dw;
-            if (w < 1.0) {
+            if (S < 0.0) {
                 double q = fmin(1.0, st.e_sb / st.e_sm) / st.e_sb;
                 double yb = y[bi];
-                const double u = 1.0 - w;
-                val[tp[0]] += -u * q * yb;
-                val[tp[1]] += u * q * yb;
-                val[tp[2]] += -u * S * q;
-                val[tp[3]] += u * S * q;
+                val[tp[0]] += -q * yb;
+                val[tp[1]] += q * yb;
+                val[tp[2]] += -S * q;
+                val[tp[3]] += S * q;
                 if (st.e_sb < st.e_sm) {
                     double dq = (y[NET_IS] <= 1e-30) ? 0.0 : -1.0 / (st.e_sm * st.e_sm);
-                    val[tp[8]] += -u * S * yb * dq;
-                    val[tp[9]] += u * S * yb * dq;
+                    val[tp[8]] += -S * yb * dq;
+                    val[tp[9]] += S * yb * dq;
                 } else {
                     double dq = (y[NET_IB] <= 1e-30) ? 0.0 : -1.0 / (st.e_sb * st.e_sb);
-                    val[tp[6]] += -u * S * yb * dq;
-                    val[tp[7]] += u * S * yb * dq;
+                    val[tp[6]] += -S * yb * dq;
+                    val[tp[7]] += S * yb * dq;
                 }
-                if (dw != 0.0) {
-                    double g = S * dw * (C_COV0 * y[si] - q * yb);
-                    val[tp[0]] += -g;
-                    val[tp[1]] += g;
-                }
-            }
-            if (w > 0.0) {
+            } else {
                 double ys = y[si];
-                val[tp[0]] += -w * C_COV0 * ys;
-                val[tp[1]] += w * C_COV0 * ys;
-                val[tp[4]] += -w * S * C_COV0;
-                val[tp[5]] += w * S * C_COV0;
+                val[tp[0]] += -C_COV0 * ys;
+                val[tp[1]] += C_COV0 * ys;
+                val[tp[4]] += -S * C_COV0;
+                val[tp[5]] += S * C_COV0;
             }
         }
     }

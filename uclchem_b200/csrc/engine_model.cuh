@@ -10,6 +10,7 @@
 //   output row layout        io.f90:59-83
 #pragma once
 #include "engine_bdf.cuh"
+#include "engine_collapse.cuh"
 
 #define JSV_STRIDE ((NET_NVAL + 31) & ~31)
 
@@ -19,7 +20,8 @@ struct RunArgs {
     long long nrun;        // cells this launch integrates: queue positions 0..nrun-1, cell = order ? order[pos] : pos
     int compact;           // 1: results are indexed by queue position (compact), 0: by cell
     const double *params;  // [UCLGPU_NPARAM][ncell]
-    const double *y0;      // [ncell][NEQ] or null
+    const double *y0;      // [ncell][NEQ] or null; with y0_index: a table, cell c starts from row y0_index[c]
+    const int *y0_index;   // [ncell] or null
     double *y_final;       // [ncell][NEQ]
     double *phys_final;    // [ncell][UCLGPU_NPHYS] or null
     int *flag;             // [ncell]
@@ -34,11 +36,10 @@ struct RunArgs {
     long long max_steps;         // uclgpu_opts.step_budget: abandon a cell (flag -5) beyond this many BDF steps; 0 = off
     const int *order;            // processing order of the cells (most expensive first) or null
     double *dump;
-    double transfer_band;        // uclgpu_opts.transfer_band: blend the three-phase transfer branches (0 = off)
 };
 
 // ---- physics hooks (thread 0) ---------------------------------------------------------------
-__device__ void ionization_dependency_dev(Scalars &st)
+__device__ __noinline__ void ionization_dependency_dev(Scalars &st)
 {
     // physics-core.f90:121-157: zeta itself is never updated there; only h2CRPRate
     if (st.p[UCL_P_IMPROVEDH2CRPDISSOCIATION] != 0.0) {
@@ -63,7 +64,7 @@ __device__ double coshinv_f_dev(float x)
     return (double)(float)log((double)(inv + sq));
 }
 
-__device__ int cshock_initialize_dev(Scalars &st)
+__device__ __noinline__ int cshock_initialize_dev(Scalars &st)
 {
     // cshock.f90:38-141
     double *p = st.p;
@@ -111,7 +112,7 @@ __device__ int cshock_initialize_dev(Scalars &st)
     return 0;
 }
 
-__device__ void cshock_update_physics_dev(Scalars &st)
+__device__ __noinline__ void cshock_update_physics_dev(Scalars &st)
 {
     // shst cshock.f90:225-252
     const double KM = 1.e5;
@@ -144,7 +145,7 @@ __device__ void cshock_update_physics_dev(Scalars &st)
     st.dusttemp = st.gastemp;
 }
 
-__device__ int initialize_physics_dev(Scalars &st)
+__device__ __noinline__ int initialize_physics_dev(Scalars &st)
 {
     const double *p = st.p;
     // coreInitializePhysics physics-core.f90:42-73
@@ -173,6 +174,8 @@ __device__ int initialize_physics_dev(Scalars &st)
         return 0;
     case UCLGPU_CSHOCK:
         return cshock_initialize_dev(st);
+    case UCLGPU_COLLAPSE: // scalar part; the enclosed-mass quadrature follows on the whole CTA (run_cell)
+        return collapse_initialize_t0(st);
     }
     return -1;
 }
@@ -205,6 +208,9 @@ __device__ void update_target_time_dev(Scalars &st)
         if (t < 2.0 * st.cs_dissipation_time)
             st.target_time = (t + st.timestep_factor * st.cs_dissipation_time) * C_SPY;
         else st.target_time = ((double)1.1f * t) * C_SPY;
+        break;
+    case UCLGPU_COLLAPSE:
+        collapse_target_time_dev(st);
         break;
     }
 }
@@ -255,7 +261,7 @@ __device__ __forceinline__ double ice_yield_integrand_dev(const Sput &q, double 
 }
 
 // iceYieldRate sputtering.f90:117-149; the trapezoid stages are summed by the whole block
-__device__ double ice_yield_rate_dev(Smem &s, Blk &b, Sput &q, double pmass, double pdens, double gastemp)
+__device__ __noinline__ double ice_yield_rate_dev(Smem &s, Blk &b, Sput &q, double pmass, double pdens, double gastemp)
 {
     const double ebind = (double)0.53f * 1.6e-12;
     const double target_mass = (double)18.0f * C_MH;
@@ -296,7 +302,7 @@ __device__ double ice_yield_rate_dev(Smem &s, Blk &b, Sput &q, double pmass, dou
 }
 
 // cshock sublimation -> sputterIces, cshock.f90:211-219, sputtering.f90:65-112
-__device__ void cshock_sublimation_dev(Smem &s, Blk &b)
+__device__ __noinline__ void cshock_sublimation_dev(Smem &s, Blk &b)
 {
     Scalars &st = s.st;
     const int tid = threadIdx.x;
@@ -347,7 +353,7 @@ __device__ void cshock_sublimation_dev(Smem &s, Blk &b)
 // ---- chemistry -------------------------------------------------------------------------------------
 // initializeChemistry chemistry.f90:57-105.  Absent elements carry index NSPEC (the density
 // slot): they are written there and then overwritten.  Thread 0, after the fill.
-__device__ void initialize_abundances_t0(Smem &s)
+__device__ __noinline__ void initialize_abundances_t0(Smem &s)
 {
     const double *p = s.st.p;
     double *a = s.abund;
@@ -456,7 +462,7 @@ __device__ int update_chemistry_dev(Smem &s, Blk &b)
     return 0;
 }
 
-__device__ void output_row_dev(Smem &s, const RunArgs &a, long long cell, int dtime)
+__device__ __noinline__ void output_row_dev(Smem &s, const RunArgs &a, long long cell, int dtime)
 {
     // io.f90:59-98; dtime is 1-based
     const Scalars &st = s.st;
@@ -490,7 +496,6 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
     st.abstol_factor = st.p[UCL_P_ABSTOL_FACTOR];
     st.mxstep = (int)st.p[UCL_P_MXSTEP];
     st.step_budget = a.max_steps;
-    st.transfer_band = a.transfer_band;
     st.rtol = st.p[UCL_P_RELTOL];
     st.last_temp = 99.0e99;
     st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;
@@ -501,6 +506,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
     st.cyc_total = clock64();
     st.flag = initialize_physics_dev(st);
     T0_END
+    if (a.kind == UCLGPU_COLLAPSE && st.flag == 0) collapse_initialize_dev(s, b);
     int flag = 0;
     int dtime = 1;
     const bool want_traj = a.phys_traj || a.chem_traj || a.rates_traj;
@@ -511,7 +517,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
         T0_BEGIN
         initialize_abundances_t0(s);
         T0_END
-        if (a.y0 && tid < NSPEC) s.abund[tid] = a.y0[(size_t)cell * NEQ + tid];
+        if (a.y0 && tid < NSPEC) s.abund[tid] = a.y0[(size_t)(a.y0_index ? a.y0_index[cell] : cell) * NEQ + tid];
         BLOCK_SYNC();
         if (want_traj) {
             if (dtime > a.timepoints + 1) flag = UCLGPU_NOT_ENOUGH_TIMEPOINTS_ERROR;
@@ -536,6 +542,7 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
             st.time_in_years = st.target_time / C_SPY;
             update_physics_dev(st);
             T0_END
+            if (st.kind == UCLGPU_COLLAPSE) collapse_update_physics_dev(s, b); // modelUpdatePhysics on the whole CTA
             if (st.kind == UCLGPU_CSHOCK) cshock_sublimation_dev(s, b);
             if (want_traj) {
                 if (dtime > a.timepoints + 1) flag = UCLGPU_NOT_ENOUGH_TIMEPOINTS_ERROR;

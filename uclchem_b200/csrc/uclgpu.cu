@@ -88,7 +88,6 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         st.hist_valid = 0;
         st.use_tcrit = 0;
         st.step_budget = 0;
-        st.transfer_band = 0.0;
         st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = st.cyc_total = 0;
         initialize_physics_dev(st);
         T0_END
@@ -332,7 +331,6 @@ static int launch_integrate(Device &d, const RunArgs &a)
     aa.jsave = d.jsave;
     if (getenv("UCLGPU_MAX_STEPS")) aa.max_steps = atoll(getenv("UCLGPU_MAX_STEPS"));
     if (getenv("UCLGPU_WARM")) aa.warm_restart = atoi(getenv("UCLGPU_WARM"));
-    if (getenv("UCLGPU_TRANSFER_BAND")) aa.transfer_band = atof(getenv("UCLGPU_TRANSFER_BAND"));
     // debug: UCLGPU_TRACE=<records> UCLGPU_TRACE_FILE=<path> dumps cell 0's Newton iterations
     double *d_trace = nullptr;
     const char *tr = getenv("UCLGPU_TRACE");
@@ -455,6 +453,7 @@ extern "C" int uclgpu_last_kernel_ms(int dev, double *ms, int64_t *launches)
 // reads cell = order[queue position]); results are COMPACT, indexed by queue position, so that one contiguous
 // D2H copy per array brings back exactly this chunk's rows and the host scatters them into the caller's arrays.
 struct DevBuf {
+    int *y0_index = nullptr;
     double *params = nullptr, *y0 = nullptr, *y_final = nullptr, *phys = nullptr, *ptraj = nullptr, *ctraj = nullptr,
            *rtraj = nullptr, *tdiss = nullptr;
     int32_t *flag = nullptr;
@@ -472,8 +471,8 @@ struct DevBuf {
     void release()
     {
         release_chunk();
-        cudaFree(params); cudaFree(y0);
-        params = y0 = nullptr;
+        cudaFree(params); cudaFree(y0); cudaFree(y0_index);
+        params = y0 = nullptr; y0_index = nullptr;
     }
 };
 
@@ -490,12 +489,18 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
         if (rc) return rc;
     }
     if (ncell < 0 || ncell > INT32_MAX || !params || !y_final || !flag) return UCLGPU_ERR_BAD_ARGUMENT;
-    if ((int)kind < 0 || (int)kind > 2) return UCLGPU_ERR_BAD_ARGUMENT;
+    if ((int)kind < 0 || (int)kind > UCLGPU_COLLAPSE) return UCLGPU_ERR_BAD_ARGUMENT;
     if (ncell == 0) return 0;
     const int nd = (int)g_dev.size();
     const size_t T1 = opts ? (size_t)opts->timepoints + 1 : 0;
     const bool want_p = opts && opts->physics_traj, want_c = opts && opts->chem_traj, want_r = opts && opts->rates_traj;
     const bool want_t = opts && opts->dissipation_time;
+    const int32_t *y0_index = (opts && y0) ? opts->y0_index : nullptr;
+    if (y0_index) {
+        if (opts->ny0 <= 0) return UCLGPU_ERR_BAD_ARGUMENT;
+        for (int64_t c = 0; c < ncell; c++)
+            if (y0_index[c] < 0 || y0_index[c] >= opts->ny0) return UCLGPU_ERR_BAD_ARGUMENT;
+    }
     const std::vector<int> ord = cost_order(params, ncell, opts ? opts->cost_hint : nullptr);
     // bytes of COMPACT result storage per cell on the device
     const size_t per_cell = sizeof(double) * (NEQ + UCLGPU_NPHYS + 1) + sizeof(int32_t) + sizeof(int) + sizeof(uclgpu_stats) +
@@ -515,8 +520,13 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
             CK(cudaMalloc(&B.params, sizeof(double) * UCLGPU_NPARAM * ncell));
             CK(cudaMemcpyAsync(B.params, params, sizeof(double) * UCLGPU_NPARAM * ncell, cudaMemcpyHostToDevice, d.stream));
             if (y0) {
-                CK(cudaMalloc(&B.y0, sizeof(double) * NEQ * ncell));
-                CK(cudaMemcpyAsync(B.y0, y0, sizeof(double) * NEQ * ncell, cudaMemcpyHostToDevice, d.stream));
+                const size_t rows = y0_index ? (size_t)opts->ny0 : (size_t)ncell;
+                CK(cudaMalloc(&B.y0, sizeof(double) * NEQ * rows));
+                CK(cudaMemcpyAsync(B.y0, y0, sizeof(double) * NEQ * rows, cudaMemcpyHostToDevice, d.stream));
+                if (y0_index) {
+                    CK(cudaMalloc(&B.y0_index, sizeof(int) * ncell));
+                    CK(cudaMemcpyAsync(B.y0_index, y0_index, sizeof(int) * ncell, cudaMemcpyHostToDevice, d.stream));
+                }
             }
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -550,11 +560,10 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
                 RunArgs a;
                 memset(&a, 0, sizeof(a));
                 a.kind = (int)kind; a.ncell = ncell; a.nrun = (long long)n; a.compact = 1; a.order = B.order;
-                a.params = B.params; a.y0 = B.y0; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
+                a.params = B.params; a.y0 = B.y0; a.y0_index = B.y0_index; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
                 if (opts) {
                     a.max_steps = opts->step_budget;
                     a.timepoints = opts->timepoints;
-                    a.transfer_band = opts->transfer_band;
                     if (want_p) { CK(cudaMalloc(&B.ptraj, sizeof(double) * UCLGPU_NPHYS * T1 * n)); CK(cudaMemsetAsync(B.ptraj, 0, sizeof(double) * UCLGPU_NPHYS * T1 * n, d.stream)); a.phys_traj = B.ptraj; }
                     if (want_c) { CK(cudaMalloc(&B.ctraj, sizeof(double) * NSPEC * T1 * n)); CK(cudaMemsetAsync(B.ctraj, 0, sizeof(double) * NSPEC * T1 * n, d.stream)); a.chem_traj = B.ctraj; }
                     if (want_r) { CK(cudaMalloc(&B.rtraj, sizeof(double) * NREAC * T1 * n)); CK(cudaMemsetAsync(B.rtraj, 0, sizeof(double) * NREAC * T1 * n, d.stream)); a.rates_traj = B.rtraj; }

@@ -1,8 +1,8 @@
 """Host-side mirror of ``uclchem.model`` for the GPU path.
 
 Same names, argument meaning and return conventions as the reference
-(``src/uclchem/model.py``: ``cloud`` :227-316, ``hot_core`` :429-524, ``cshock``
-:527-644), but the work goes through the C ABI of ``include/uclgpu.h`` instead of
+(``src/uclchem/model.py``: ``cloud`` :227-316, ``collapse`` :319-426, ``hot_core`` :429-524,
+``cshock`` :527-644), but the work goes through the C ABI of ``include/uclgpu.h`` instead of
 ``uclchemwrap``.  On top of the per-model functions the module adds what the
 reference leaves to user scripts (``scripts/grid.py:41-59``): ``cloud_grid``,
 ``hot_core_grid`` and ``cshock_grid`` integrate a whole table of models in one call.
@@ -148,6 +148,30 @@ def cloud(param_dict=None, out_species=None, return_array=False, return_datafram
                        starting_chemistry, timepoints, {})
 
 
+COLLAPSE_MODES = {"BE1.1": 1, "BE4": 2, "filament": 3, "ambipolar": 4}   # model.py:361
+
+
+def _collapse_mode(collapse):
+    try:
+        return COLLAPSE_MODES[collapse]
+    except (KeyError, TypeError):
+        raise ValueError("collapse must be one of 'BE1.1', 'BE4', 'filament', or 'ambipolar'")
+
+
+def collapse(collapse, physics_output, param_dict=None, out_species=None, return_array=False, return_dataframe=False,
+             return_rates=False, starting_chemistry=None, timepoints=TIMEPOINTS):
+    """Collapsing prestellar core, Priestley et al. 2018 (model.py:319-426, collapse.f90).  `collapse` is one of
+    'BE1.1', 'BE4', 'filament', 'ambipolar'; the Bonnor-Ebert modes set their own final time (0.97 of the fit's
+    time span).  `physics_output` (the reference's per-interval dump of radius / density / velocity to a text
+    file) is not written by the GPU path: pass None and read the density from the physics trajectory."""
+    mode = _collapse_mode(collapse)
+    if physics_output is not None:
+        raise NotImplementedError("physics_output is not written by the GPU path; use return_array / return_dataframe "
+                                  "and read Density from the physics output")
+    return _run_single("collapse", param_dict, out_species, return_array, return_dataframe, return_rates,
+                       starting_chemistry, timepoints, {"collapse_mode": mode})
+
+
 def hot_core(temp_indx, max_temperature, param_dict=None, out_species=None, return_array=False,
              return_dataframe=False, return_rates=False, starting_chemistry=None, timepoints=TIMEPOINTS):
     """Hot core / hot corino warm-up (model.py:429-524)."""
@@ -214,6 +238,14 @@ def cloud_grid(param_dict, starting_chemistry=None, out_species=None, return_arr
     (``physics_array`` [timepoints+1, ncell, 8], ``chemical_abun_array`` [timepoints+1, ncell, nspec],
     ``rates_array`` with ``return_rates``) and ``nrows``, the number of filled rows per cell."""
     return _run_grid("cloud", param_dict, starting_chemistry, {}, out_species, return_array, return_rates, timepoints)
+
+
+def collapse_grid(collapse, param_dict, starting_chemistry=None, out_species=None, return_array=False,
+                  return_rates=False, timepoints=TIMEPOINTS):
+    """A grid of collapse models; `collapse` is one name or one name per cell."""
+    modes = [_collapse_mode(c) for c in collapse] if not isinstance(collapse, str) else _collapse_mode(collapse)
+    return _run_grid("collapse", param_dict, starting_chemistry, {"collapse_mode": modes}, out_species, return_array,
+                     return_rates, timepoints)
 
 
 def hot_core_grid(temp_indx, max_temperature, param_dict, starting_chemistry=None, out_species=None,

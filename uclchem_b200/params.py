@@ -29,11 +29,12 @@ _PARAMS = [
     ("uv_yield", 0.03), ("phi", 1.0e5), ("uvcreff", 1.0e-3), ("omega", 0.5),
     ("temp_indx", 1.0), ("max_temperature", 300.0),
     ("shock_vel", 0.0), ("timestep_factor", 0.01), ("minimum_temperature", 0.0),
+    ("collapse_mode", 0.0),
 ]
 PARAM_NAMES = [k for k, _ in _PARAMS]
 PARAM_INDEX = {k: i for i, k in enumerate(PARAM_NAMES)}
 NPARAM = len(_PARAMS)
-assert NPARAM == 64
+assert NPARAM == 65
 
 # keys the reference's parser accepts but that do not influence the hot path
 # (file names, output cadence); they are tolerated and ignored by the grid API.
@@ -45,7 +46,7 @@ _IGNORED = {
 # REAL(dp) :: x = <single-precision literal>  ->  value is float32-rounded
 _F32_DEFAULTS = {"rout": 0.05, "fhe": 0.1, "epsilon": 0.01, "uv_yield": 0.03}
 
-MODEL_KINDS = {"cloud": 0, "hot_core": 1, "cshock": 2}
+MODEL_KINDS = {"cloud": 0, "hot_core": 1, "cshock": 2, "collapse": 3}
 
 
 def default_params(ncell: int = 1) -> np.ndarray:

@@ -1,9 +1,10 @@
 """Sharding of a grid over ranks (one process per GPU).
 
-Cells are independent, so a grid is cut into contiguous shards and each
-rank integrates its own; nothing crosses NVLink during integration.  The only collective
-is the final gather of results to rank 0 (``torch.distributed``; NCCL on the GPU box, gloo
-in the CPU tests)."""
+Cells are independent, so every rank integrates its own cells and nothing crosses
+NVLink during integration.  The only collective is the gather of results to rank 0
+(``torch.distributed``; NCCL on the GPU box, gloo in the CPU tests).  Inside one process the C ABI
+itself deals a grid over the devices it was bound to (``uclgpu_run_grid``, round-robin over the
+cost-sorted cells); these helpers are for the one-process-per-GPU launch of ``bench.py``."""
 from __future__ import annotations
 
 
@@ -28,3 +29,30 @@ def gather_results(local, ncell: int, rank: int, world: int):
     if rank != 0:
         return None
     return torch.cat([b[: hi - lo] for b, (lo, hi) in zip(bufs, sizes)], dim=0)
+
+
+def gather_rows(local, rank: int, world: int, out=None):
+    """Gather equally sized per-rank blocks [n, k] to rank 0.  Returns the list of `world` blocks on
+    rank 0 (in rank order; `out` may supply preallocated receive buffers) and None elsewhere."""
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return [local]
+    bufs = None
+    if rank == 0:
+        bufs = out if out is not None else [torch.empty_like(local) for _ in range(world)]
+    dist.gather(local, bufs, dst=0)
+    return bufs
+
+
+def max_over_ranks(values, world: int, device=None):
+    """Element-wise maximum of a small list of floats over all ranks (device-side timing is reported as
+    the slowest rank's)."""
+    import torch
+    import torch.distributed as dist
+
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
