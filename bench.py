@@ -533,6 +533,8 @@ def main():
 
     for _ in range(a.warmup):
         warm.run(20000)
+        if world > 1:   # the communicator is created lazily by the first collective: not inside the timed region
+            gather_rows(stage, rank, world, out=gathered)
         flush.fill_(1)
     log(f"warm-up done ({a.warmup} x {warm.n} cells); timing {a.steps} steps of {first.n} cells")
 

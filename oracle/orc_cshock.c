@@ -263,3 +263,89 @@ void orc_cshock_sublimation(orc_model *m)
     for (int i = 0; i < neq; i++)
         if (m->abund[i] < 1.0e-50) m->abund[i] = 0.0;
 }
+
+
+/* ---- jshock_mod, jshock.f90 (James et al. 2020 J-shock parameterisation; single point) -------------------- */
+#define JF(x) ((double)(x##f))
+
+/* jshock.f90:29-78 */
+int orc_jshock_initialize(orc_model *m)
+{
+    double *p = m->p;
+    m->vs = p[UCL_P_VS];
+    m->cloudsize = (p[UCL_P_ROUT] - p[UCL_P_RIN]) * PC;
+    if (p[UCL_P_FREEFALL] != 0.0) p[UCL_P_FREEFALL] = 0.0;
+    if (p[UCL_P_POINTS] > 1) return -1;
+    const double vs = m->vs, id = p[UCL_P_INITIALDENS];
+    m->density = id;
+    m->js_max_temp = JF(5e3) * pow(vs / 10, 2.0);
+    m->current_time_old = 0.0;
+    double poly = JF(-2.058e-07) * pow(vs, 4.0) + JF(3.844e-05) * pow(vs, 3.0) - JF(0.002478) * pow(vs, 2.0) + JF(0.06183) * vs -
+                  JF(0.4254);
+    m->js_vmin = pow(pow(poly, 2.0), (double)0.5f);
+    /* mfp = ((SQRT(2.0)*(1e3)*(pi*(2.4e-8)**2))**(-1))/1d4: SQRT(2.0), 1e3 and 2.4e-8 are single precision;
+     * pi is the double parameter (single-precision literal value), so the product is double */
+    double inner = (double)(sqrtf(2.0f) * 1e3f) * (PI_F * (double)(2.4e-8f * 2.4e-8f));
+    m->js_tshock = ((1.0 / inner) / 1e4) / (vs * 1e5);
+    m->js_tcool = (1 / id) * 1e6 * (60 * 60 * 24 * 365);
+    m->js_max_dens = vs * id * 1e2;
+    m->js_t_lambda = log(m->js_max_temp / p[UCL_P_INITIALTEMP]);
+    m->js_n_lambda = log(m->js_max_dens / id);
+    m->js_v0 = 0.0;
+    return 0;
+}
+
+/* jshock.f90:85-97 */
+void orc_jshock_update_target_time(orc_model *m)
+{
+    double t = m->time_in_years;
+    if (t > JF(1e6))
+        m->target_time = (t + JF(1e5)) * SECONDS_PER_YEAR;
+    else if (t > 1.0e4)
+        m->target_time = (t + 1000) * SECONDS_PER_YEAR;
+    else if (t > 1.0e3)
+        m->target_time = (t + JF(100.)) * SECONDS_PER_YEAR;
+    else if (t * SECONDS_PER_YEAR < m->js_tshock)
+        m->target_time = m->current_time + JF(0.05) * m->js_tshock;
+    else
+        m->target_time = JF(1.1) * m->current_time;
+}
+
+/* jshock.f90:102-135 */
+void orc_jshock_update_physics(orc_model *m)
+{
+    const double *p = m->p;
+    const double ct = m->current_time, id = p[UCL_P_INITIALDENS];
+    double v0 = m->vs * exp(log(m->js_vmin / m->vs) * (ct / (p[UCL_P_FINALTIME] * 60 * 60 * 24 * 365)));
+    if (v0 < m->js_vmin) v0 = m->js_vmin;
+    m->js_v0 = v0;
+    double tn;
+    if (ct <= m->js_tshock) {
+        tn = pow(ct / m->js_tshock, 2.0) * m->js_max_temp + p[UCL_P_INITIALTEMP];
+        m->density = pow(ct / m->js_tshock, 3.0) * (4 * id);
+        if (m->density < id) m->density = id;
+    } else if (ct > m->js_tshock && ct <= m->js_tcool) {
+        tn = m->js_max_temp * exp(-m->js_t_lambda * (ct / m->js_tcool));
+        m->density = (4 * id) * exp(m->js_n_lambda * (ct / m->js_tcool));
+        if (tn <= 10) tn = 10;
+        if (m->density > m->js_max_dens) m->density = m->js_max_dens;
+    } else {
+        tn = 10;
+        m->density = m->js_max_dens;
+    }
+    m->gastemp = tn;
+    m->dusttemp = m->gastemp;
+}
+
+/* jshock.f90:143-152 */
+void orc_jshock_sublimation(orc_model *m)
+{
+    const orc_network *net = m->net;
+    int neq = net->nspec + 1;
+    double time_delta = m->current_time - m->current_time_old;
+    double total = 0.0;
+    for (int k = 0; k < net->nice; k++) total += m->abund[net->ice_list[k]];
+    if (total > 1e-25 && m->js_v0 > 0) sputter_ices(m, m->js_v0, m->gastemp, m->density, time_delta);
+    for (int i = 0; i < neq; i++)
+        if (m->abund[i] < 1.0e-50) m->abund[i] = 0.0;
+}

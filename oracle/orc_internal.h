@@ -34,6 +34,8 @@ typedef struct orc_model {
         cs_dissipation_time, cs_max_temp, cs_drift_vel, cs_zn, cs_vn, cs_tn, cs_ts, cs_initial_dens_cs,
         cs_grain_number_density, cs_grain_radius_cgs;
     int cs_coflag;
+    /* jshock.f90 module state */
+    double js_max_temp, js_vmin, js_tshock, js_tcool, js_max_dens, js_t_lambda, js_n_lambda, js_v0;
     /* collapse.f90 module state */
     int collapse_mode;
     double col_max_time, col_parcel_radius, col_mass_in_radius;
@@ -60,6 +62,10 @@ int orc_cshock_initialize(orc_model *m);
 void orc_cshock_update_target_time(orc_model *m);
 void orc_cshock_update_physics(orc_model *m);
 void orc_cshock_sublimation(orc_model *m);
+int orc_jshock_initialize(orc_model *m);
+void orc_jshock_update_target_time(orc_model *m);
+void orc_jshock_update_physics(orc_model *m);
+void orc_jshock_sublimation(orc_model *m);
 
 /* orc_collapse.c */
 int orc_collapse_initialize(orc_model *m);

@@ -114,6 +114,8 @@ static int model_initialize_physics(orc_model *m)
         return orc_cshock_initialize(m);
     case UCLGPU_COLLAPSE:
         return orc_collapse_initialize(m);
+    case UCLGPU_JSHOCK:
+        return orc_jshock_initialize(m);
     }
     return -1;
 }
@@ -156,6 +158,9 @@ static void update_target_time(orc_model *m)
     case UCLGPU_COLLAPSE:
         orc_collapse_update_target_time(m);
         break;
+    case UCLGPU_JSHOCK:
+        orc_jshock_update_target_time(m);
+        break;
     }
 }
 
@@ -182,6 +187,9 @@ static void model_update_physics(orc_model *m)
     case UCLGPU_COLLAPSE:
         orc_collapse_update_physics(m);
         break;
+    case UCLGPU_JSHOCK:
+        orc_jshock_update_physics(m);
+        break;
     }
 }
 
@@ -189,6 +197,7 @@ static void sublimation(orc_model *m)
 {
     /* cloud.f90:62-65 no-op; hotcore.f90:92-107 no-op for THREE_PHASE networks */
     if (m->kind == UCLGPU_CSHOCK) orc_cshock_sublimation(m);
+    if (m->kind == UCLGPU_JSHOCK) orc_jshock_sublimation(m); /* jshock.f90:143-152 */
 }
 
 /* initializeChemistry, chemistry.f90:46-141.  Absent elements carry index nspec

@@ -5,7 +5,7 @@ import pytest
 from conftest import GOLDEN, STATIC, max_dex
 
 from uclchem_b200 import model
-from uclchem_b200.params import params_from_dict
+from uclchem_b200.params import PARAM_INDEX, params_from_dict
 
 pytestmark = pytest.mark.gpu
 
@@ -309,3 +309,24 @@ def test_collapse_model_against_oracle(lib, oracle):
     assert out["phys_final"][0, 0] > 0.97 * 1.855e5 - 1.0       # BE4 ignores finalTime (collapse.f90:39-41)
     res = model.collapse("BE4", None, param_dict={"rout": 0.2, "baseAv": 1.0}, out_species=["CO"])
     assert res[0] == 0 and res[1] == pytest.approx(out["y_final"][0, 49], rel=1e-12)
+
+
+def test_jshock_model_against_oracle(lib, oracle):
+    """jshock.f90 (no golden exists: parity pinned only via the self-validated oracle): heating to 5e3 (v/10)^2 K
+    inside the shock width, cooling / compression phase, sputtering with the shock velocity."""
+    sc = np.load(GOLDEN / "shockstart.npy")
+    p = params_from_dict({"initialDens": [1e3, 1e4], "initialTemp": 10.0, "finalTime": [1e4, 1e3], "shock_vel": [10.0, 30.0],
+                          "reltol": 1e-6, "abstol_min": 1e-20})
+    y0 = np.stack([np.append(sc, 1e3), np.append(sc, 1e4)])
+    out = lib.run_grid(4, p, y0=y0, timepoints=1000, want_physics=True, want_chem=True)
+    assert (out["flag"] == 0).all()
+    for c in range(2):
+        r = oracle.run_model(4, p[:, c], y0=y0[c], timepoints=1000)
+        n = r["physics"].shape[0]
+        assert r["flag"] == 0 and out["stats"][c][7] == n - 1
+        np.testing.assert_allclose(out["physics"][c, :n, :4], r["physics"][:, :4], rtol=1e-9)   # time, density, temperatures
+        assert out["physics"][c, :n, 2].max() == pytest.approx(5e3 * (p[PARAM_INDEX["shock_vel"], c] / 10) ** 2, rel=1e-3)
+        assert max_dex(out["y_final"][c, :335], r["y_final"][:335]) < DEX_TOL, c
+    res = model.jshock(10.0, param_dict={"initialDens": 1e3, "finalTime": 1.0, "reltol": 1e-6, "abstol_min": 1e-20},
+                       return_array=True, starting_chemistry=sc)
+    assert len(res) == 5 and res[-1] == 0

@@ -80,6 +80,8 @@ struct Scalars {
     double cs_dlength, cs_z1, cs_z2, cs_z3, cs_v0, cs_at, cs_vn0, cs_zn0, cs_dissipation_time, cs_max_temp,
         cs_drift_vel, cs_zn, cs_vn;
     int temp_indx;
+    // jshock.f90 module state
+    double js_max_temp, js_vmin, js_tshock, js_tcool, js_max_dens, js_t_lambda, js_n_lambda, js_v0;
     // collapse.f90 module state
     int col_mode;
     double col_max_time, col_parcel_radius, col_mass_in_radius;

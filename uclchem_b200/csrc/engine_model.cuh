@@ -145,6 +145,61 @@ __device__ __noinline__ void cshock_update_physics_dev(Scalars &st)
     st.dusttemp = st.gastemp;
 }
 
+// ---- jshock.f90 (James et al. 2020 J-shock parameterisation), thread 0 ------------------------------------
+__device__ __noinline__ int jshock_initialize_dev(Scalars &st)
+{
+    // jshock.f90:29-78
+    double *p = st.p;
+    st.vs = p[UCL_P_VS];
+    st.cloudsize = (p[UCL_P_ROUT] - p[UCL_P_RIN]) * C_PC;
+    if (p[UCL_P_FREEFALL] != 0.0) p[UCL_P_FREEFALL] = 0.0;
+    if (p[UCL_P_POINTS] > 1) return -1;
+    const double vs = st.vs, id = p[UCL_P_INITIALDENS];
+    st.density = id;
+    st.js_max_temp = (double)5e3f * ((vs / 10) * (vs / 10));
+    st.current_time_old = 0.0;
+    const double v2 = vs * vs;
+    const double poly = (double)-2.058e-07f * (v2 * v2) + (double)3.844e-05f * (v2 * vs) - (double)0.002478f * v2 +
+                        (double)0.06183f * vs - (double)0.4254f;
+    st.js_vmin = pow(poly * poly, (double)0.5f);
+    // mean free path / shock width: the literals of the product are single precision, pi is a double parameter
+    const double inner = (double)(sqrtf(2.0f) * 1e3f) * (C_PI * (double)(2.4e-8f * 2.4e-8f));
+    st.js_tshock = ((1.0 / inner) / 1e4) / (vs * 1e5);
+    st.js_tcool = (1 / id) * 1e6 * (60 * 60 * 24 * 365);
+    st.js_max_dens = vs * id * 1e2;
+    st.js_t_lambda = log(st.js_max_temp / p[UCL_P_INITIALTEMP]);
+    st.js_n_lambda = log(st.js_max_dens / id);
+    st.js_v0 = 0.0;
+    return 0;
+}
+
+__device__ __noinline__ void jshock_update_physics_dev(Scalars &st)
+{
+    // jshock.f90:102-135
+    const double *p = st.p;
+    const double ct = st.current_time, id = p[UCL_P_INITIALDENS];
+    double v0 = st.vs * exp(log(st.js_vmin / st.vs) * (ct / (p[UCL_P_FINALTIME] * 60 * 60 * 24 * 365)));
+    if (v0 < st.js_vmin) v0 = st.js_vmin;
+    st.js_v0 = v0;
+    double tn;
+    if (ct <= st.js_tshock) {
+        const double x = ct / st.js_tshock;
+        tn = (x * x) * st.js_max_temp + p[UCL_P_INITIALTEMP];
+        st.density = (x * x * x) * (4 * id);
+        if (st.density < id) st.density = id;
+    } else if (ct <= st.js_tcool) {
+        tn = st.js_max_temp * exp(-st.js_t_lambda * (ct / st.js_tcool));
+        st.density = (4 * id) * exp(st.js_n_lambda * (ct / st.js_tcool));
+        if (tn <= 10) tn = 10;
+        if (st.density > st.js_max_dens) st.density = st.js_max_dens;
+    } else {
+        tn = 10;
+        st.density = st.js_max_dens;
+    }
+    st.gastemp = tn;
+    st.dusttemp = tn;
+}
+
 __device__ __noinline__ int initialize_physics_dev(Scalars &st)
 {
     const double *p = st.p;
@@ -176,6 +231,8 @@ __device__ __noinline__ int initialize_physics_dev(Scalars &st)
         return cshock_initialize_dev(st);
     case UCLGPU_COLLAPSE: // scalar part; the enclosed-mass quadrature follows on the whole CTA (run_cell)
         return collapse_initialize_t0(st);
+    case UCLGPU_JSHOCK:
+        return jshock_initialize_dev(st);
     }
     return -1;
 }
@@ -212,6 +269,13 @@ __device__ void update_target_time_dev(Scalars &st)
     case UCLGPU_COLLAPSE:
         collapse_target_time_dev(st);
         break;
+    case UCLGPU_JSHOCK: // jshock.f90:85-97
+        if (t > (double)1e6f) st.target_time = (t + (double)1e5f) * C_SPY;
+        else if (t > 1.0e4) st.target_time = (t + 1000) * C_SPY;
+        else if (t > 1.0e3) st.target_time = (t + (double)100.f) * C_SPY;
+        else if (t * C_SPY < st.js_tshock) st.target_time = st.current_time + (double)0.05f * st.js_tshock;
+        else st.target_time = (double)1.1f * st.current_time;
+        break;
     }
 }
 
@@ -239,6 +303,9 @@ __device__ void update_physics_dev(Scalars &st)
     }
     case UCLGPU_CSHOCK:
         cshock_update_physics_dev(st);
+        break;
+    case UCLGPU_JSHOCK:
+        jshock_update_physics_dev(st);
         break;
     default:
         break;
@@ -301,16 +368,17 @@ __device__ __noinline__ double ice_yield_rate_dev(Smem &s, Blk &b, Sput &q, doub
     return r * pdens;
 }
 
-// cshock sublimation -> sputterIces, cshock.f90:211-219, sputtering.f90:65-112
-__device__ __noinline__ void cshock_sublimation_dev(Smem &s, Blk &b)
+// shock sublimation -> sputterIces (cshock.f90:211-219 with the drift velocity, jshock.f90:143-152 with the shock
+// velocity v0), sputtering.f90:65-112
+__device__ __noinline__ void shock_sublimation_dev(Smem &s, Blk &b, double shockvel)
 {
     Scalars &st = s.st;
     const int tid = threadIdx.x;
     double t = 0.0;
     if (tid < NICE) t = s.abund[net_ice_list[tid]];
     double total = block_sum(s, b, t);
-    if (total > 1e-25 && st.cs_drift_vel > 0) {
-        const double shockvel = st.cs_drift_vel, gastemp = st.gastemp, density = st.density;
+    if (total > 1e-25 && shockvel > 0) {
+        const double gastemp = st.gastemp, density = st.density;
         Sput q;
         q.sconst = sqrt((shockvel * shockvel * 1.e5 * 1.e5) / (2.0 * gastemp * C_KBOLTZ));
         const int proj[6] = {NET_NH2, NET_NHE, NET_NC, NET_NO, NET_NSI, NET_NCO};
@@ -543,7 +611,8 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
             update_physics_dev(st);
             T0_END
             if (st.kind == UCLGPU_COLLAPSE) collapse_update_physics_dev(s, b); // modelUpdatePhysics on the whole CTA
-            if (st.kind == UCLGPU_CSHOCK) cshock_sublimation_dev(s, b);
+            if (st.kind == UCLGPU_CSHOCK) shock_sublimation_dev(s, b, st.cs_drift_vel);
+            if (st.kind == UCLGPU_JSHOCK) shock_sublimation_dev(s, b, st.js_v0);
             if (want_traj) {
                 if (dtime > a.timepoints + 1) flag = UCLGPU_NOT_ENOUGH_TIMEPOINTS_ERROR;
                 else output_row_dev(s, a, out, dtime);

@@ -489,7 +489,7 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
         if (rc) return rc;
     }
     if (ncell < 0 || ncell > INT32_MAX || !params || !y_final || !flag) return UCLGPU_ERR_BAD_ARGUMENT;
-    if ((int)kind < 0 || (int)kind > UCLGPU_COLLAPSE) return UCLGPU_ERR_BAD_ARGUMENT;
+    if ((int)kind < 0 || (int)kind > UCLGPU_JSHOCK) return UCLGPU_ERR_BAD_ARGUMENT;
     if (ncell == 0) return 0;
     const int nd = (int)g_dev.size();
     const size_t T1 = opts ? (size_t)opts->timepoints + 1 : 0;

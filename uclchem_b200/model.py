@@ -189,6 +189,14 @@ def cshock(shock_vel, timestep_factor=0.01, minimum_temperature=0.0, param_dict=
                         "minimum_temperature": minimum_temperature})
 
 
+def jshock(shock_vel, param_dict=None, out_species=None, return_array=False, return_dataframe=False,
+           return_rates=False, starting_chemistry=None, timepoints=TIMEPOINTS):
+    """J-type shock, James et al. 2020 (model.py:647-745, jshock.f90).  Unlike cshock no dissipation time is
+    returned: the tuples are those of `cloud`."""
+    return _run_single("jshock", param_dict, out_species, return_array, return_dataframe, return_rates,
+                       starting_chemistry, timepoints, {"shock_vel": shock_vel})
+
+
 # ---------------------------------------------------------------------------------------
 # grids: what scripts/grid.py does with a process pool, in one call
 # ---------------------------------------------------------------------------------------
@@ -261,3 +269,9 @@ def cshock_grid(shock_vel, param_dict, timestep_factor=0.01, minimum_temperature
                      {"shock_vel": shock_vel, "timestep_factor": timestep_factor,
                       "minimum_temperature": minimum_temperature}, out_species, return_array, return_rates,
                      timepoints)
+
+
+def jshock_grid(shock_vel, param_dict, starting_chemistry=None, out_species=None, return_array=False,
+                return_rates=False, timepoints=TIMEPOINTS):
+    return _run_grid("jshock", param_dict, starting_chemistry, {"shock_vel": shock_vel}, out_species, return_array,
+                     return_rates, timepoints)
