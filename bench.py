@@ -259,6 +259,7 @@ class StepSpec:
 class Workload:
     tag = "default"
     nslice = NSLICE
+    step_budget = STEP_BUDGET  # BDF steps per model before it is abandoned: ~10x a typical model of the workload
     disjoint_ranks = True     # ranks take different steps of one grid (False: every rank has its own grid)
 
     def step(self, k):
@@ -308,6 +309,7 @@ class Config3(Workload):
     takes 8 of the 1 000 (n_f, zeta) pairs (a fixed shuffle) with all 100 hot cores of each: 8 stage-1 models,
     then 800 hot cores whose starting states are read from the stage-1 result table by index."""
     nslice = 125
+    step_budget = 1000000     # a 1 Myr hot core is 282 output intervals, ~1.1e5 steps when nothing stalls
 
     def __init__(self, rank, world, a):
         nf, ze = np.meshgrid(10 ** np.linspace(4, 7, 40), 10 ** np.linspace(0, 2, 25), indexing="ij")
@@ -336,6 +338,7 @@ class Config4(Workload):
     """BASELINE configs[3]: 10^4 C-shocks, 100 velocities (10..45 km/s) x 100 pre-shock densities (10^3.5..10^6),
     pre-shock abundances from a free-fall collapse to each density, tolerances of notebooks/3_running_a_grid.py."""
     nslice = 10
+    step_budget = 400000      # ~240 output intervals, 3.7e4 steps for a typical shock
 
     def __init__(self, rank, world, a):
         self.vs = np.linspace(10, 45, 100)
@@ -359,14 +362,18 @@ class Config4(Workload):
 
 class Config5(Workload):
     """BASELINE configs[4]: 10^6 static clouds (100^3 over the config-2 ranges) on the network MakeRates generates
-    with add_crp_photo_to_grain (335 species / 3453 reactions), tolerances of tests/test_photo_on_grain.py."""
+    with add_crp_photo_to_grain (335 species / 3453 reactions).  Run at the DEFAULT tolerances (reltol 1e-8,
+    abstol_min 1e-25), which is stricter than SURVEY.md 8(d) asks (the reference's own test of this network loosens
+    them to 1e-5 / 1e-15): the engine's no-pivot factorisation is validated at the default tolerances only
+    (DESIGN.md section 9)."""
     tag = "crp_photo"
     nslice = 400
 
     def __init__(self, rank, world, a):
         self.axes = (10 ** np.linspace(3, 7, 100), np.linspace(10, 100, 100), 10 ** np.linspace(0, 3, 100))
         self.desc = {"workload": "config[4]: 10^6-point static cloud grid (100 n_H x 100 T x 100 zeta over the config-2 ranges), 1 Myr, "
-                                 "crp-photo network 335 species / 3453 reactions, reltol 1e-5, abstol_min 1e-15",
+                                 "crp-photo network 335 species / 3453 reactions, default tolerances (reltol 1e-8, abstol_min 1e-25: "
+                                 "stricter than the reference's test of this network, which uses 1e-5 / 1e-15)",
                      "step": "every 400th cell of the grid (2 500 cells per GPU); 400 steps cover the grid",
                      "cells_per_gpu_per_step": 2500, "cells_total": 1000000}
 
@@ -376,7 +383,7 @@ class Config5(Workload):
         d, t, z = np.unravel_index(i, (100, 100, 100))
         return StepSpec(0, params_from_dict({"initialDens": self.axes[0][d], "initialTemp": self.axes[1][t], "zeta": self.axes[2][z],
                                              "radfield": 1.0, "baseAv": 2.0, "rout": 0.05, "finalTime": 1.0e6, "freefall": False,
-                                             "endAtFinalDensity": False, "reltol": 1e-5, "abstol_min": 1e-15}))
+                                             "endAtFinalDensity": False}))
 
 
 WORKLOADS = {1: Config1, 2: Config2, 3: Config3, 4: Config4, 5: Config5}
@@ -390,8 +397,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", type=int, default=2, choices=sorted(WORKLOADS),
                     help="BASELINE.json configs[workload-1]; 2 (the 10^4 static-cloud grid) is the headline and the default")
-    ap.add_argument("--step-budget", type=int, default=STEP_BUDGET,
-                    help="BDF steps after which a cell is abandoned (flag -5, not counted); 0 = the reference's unbounded crawl")
+    ap.add_argument("--step-budget", type=int, default=-1,
+                    help="BDF steps after which a cell is abandoned (flag -5, not counted); 0 = the reference's unbounded crawl; "
+                         "default: the workload's own (about ten times what a typical model of the workload needs)")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="bound of the cpu_baseline sample")
     ap.add_argument("--cells", type=int, default=0, help="debug: override the grid size (not a valid bench line)")
     a = ap.parse_args()
@@ -399,6 +407,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     wl = WORKLOADS[a.workload](rank, world, a)
+    if a.step_budget < 0:
+        a.step_budget = wl.step_budget
     workload = dict(wl.desc)
     workload.update({"step_budget": a.step_budget,
                      "timing": "L2 flushed (256 MiB write) between timed steps; a step's inputs are read once per cell",

@@ -32,15 +32,16 @@ def generate(tag: str = "default", network_f90: str | None = None) -> Path:
     from .makerates_cuda import Generated, emit
     from .network import Network
 
-    js = _PKG / "networks" / f"{tag}.json"
+    js = _PKG / "networks" / f"{TAG_OPTIONS.get(tag, {}).get('network', tag)}.json"
     if network_f90 is not None:
         net = Network.from_network_f90(network_f90)
         js.parent.mkdir(parents=True, exist_ok=True)
         net.to_json(js)
     else:
         net = Network.from_json(js)
-    thr = TAG_OPTIONS.get(tag, {}).get("dense_threshold", 0.9)
-    return emit(Generated(net, dense_threshold=thr), CSRC / "generated" / tag, tag)
+    opt = TAG_OPTIONS.get(tag, {})
+    gen = Generated(net, dense_threshold=opt.get("dense_threshold", 0.9), factor_terms_per_lane=opt.get("factor_terms_per_lane", 8))
+    return emit(gen, CSRC / "generated" / tag, tag)
 
 
 # build variants: suffix of the library name -> extra nvcc defines.  The default build uses the product-form

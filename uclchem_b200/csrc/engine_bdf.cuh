@@ -772,6 +772,9 @@ __device__ __noinline__ int bdf_integrate(Smem &s, Blk &b, double tout, bool war
     for (;;) {
         if (!first) {
             if (st.nst_call >= st.mxstep) { istate = -1; break; }
+            // uclgpu_opts.step_budget: stop inside the call too (attempts count: a call that alternates accepted and
+            // failed steps would otherwise overshoot the budget by up to 16 x MXSTEP attempts)
+            if (st.step_budget > 0 && st.nst + st.netf + st.ncfn > st.step_budget) { istate = -1; break; }
             double badw = 0.0;
             if (tid < NEQ) {
                 double e = st.rtol * fabs(s.yh[0][tid]) + s.atol[tid];

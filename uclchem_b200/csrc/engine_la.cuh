@@ -499,7 +499,10 @@ __device__ __noinline__ bool factor_p(Smem &s, Blk &b)
     const int tid = threadIdx.x;
     double *val = s.val;
     TIMER_START
-    run_levels<8>(
+#ifndef UCLGPU_FACTOR_U
+#define UCLGPU_FACTOR_U 8 /* terms per lane and batch of the factor program (build.py TAG_OPTIONS) */
+#endif
+    run_levels<UCLGPU_FACTOR_U>(
         net_factor_desc, net_factor_terms, net_factor_units, NET_FACTOR_NUNITS,
         [&](uint32_t t) { return make_double2(val[t >> 16], val[t & 0xFFFFu]); },
         [](uint32_t target) { return (uint32_t)__ldg(net_factor_diag + target); },

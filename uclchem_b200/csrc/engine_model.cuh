@@ -503,7 +503,7 @@ __device__ int update_chemistry_dev(Smem &s, Blk &b)
         const bool warm = st.use_tcrit && st.hist_valid;
         int istate = bdf_integrate(s, b, st.target_time, warm);
         if (istate == -3) return UCLGPU_INT_UNRECOVERABLE_ERROR;
-        if (st.step_budget > 0 && st.nst > st.step_budget) return UCLGPU_INT_TOO_MANY_FAILS_ERROR;
+        if (st.step_budget > 0 && st.nst + st.netf + st.ncfn > st.step_budget) return UCLGPU_INT_TOO_MANY_FAILS_ERROR;
         // integrateODESystem chemistry.f90:256-291
         if (st.p[UCL_P_ENFORCECHARGECONSERVATION] != 0.0) {
             double q = 0.0;

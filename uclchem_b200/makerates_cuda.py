@@ -103,7 +103,7 @@ class TeamProgram:
 class Generated:
     """All tables of one network, in memory (also used by the CPU tests)."""
 
-    def __init__(self, net: Network, dense_threshold: float = 0.9):
+    def __init__(self, net: Network, dense_threshold: float = 0.9, factor_terms_per_lane: int = 8):
         self.net = net
         self.sym = sym = symbolic.build(net, dense_threshold)
         neq = sym.neq
@@ -172,7 +172,7 @@ class Generated:
             for e in range(len(L["target"])):
                 a, b = L["ptr"][e], L["ptr"][e + 1]
                 items.append((int(L["target"][e]), [(int(l) << 16) | int(u) for l, u in zip(L["tl"][a:b], L["tu"][a:b])]))
-            self.factor.append((TeamProgram(items, terms_per_lane=8), {int(t): int(d) for t, d in zip(L["target"], L["diag"])}))
+            self.factor.append((TeamProgram(items, terms_per_lane=factor_terms_per_lane), {int(t): int(d) for t, d in zip(L["target"], L["diag"])}))
         # solves
         def lvl(Ls):
             out = []
