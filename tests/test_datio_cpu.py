@@ -62,7 +62,8 @@ class _OracleBackedLibrary:
         self._nstat, self._iint = len(STAT_FIELDS), STAT_FIELDS.index("nintervals")
 
     def run_grid(self, kind, params, y0=None, timepoints=0, want_physics=False, want_chem=False, want_rates=False,
-                 step_budget=0):
+                 step_budget=0, coefficients=None):
+        assert not coefficients, "the double has no per-reaction overrides"
         ncell = params.shape[1]
         tp = max(timepoints, 1)
         out = {"y_final": np.zeros((ncell, self.neq)), "phys_final": np.zeros((ncell, 8)),
@@ -72,9 +73,11 @@ class _OracleBackedLibrary:
             out["physics"] = np.zeros((ncell, timepoints + 1, 8))
         if want_chem:
             out["abund"] = np.zeros((ncell, timepoints + 1, self.nspec))
+        if want_rates:
+            out["rates"] = np.zeros((ncell, timepoints + 1, self.nreac))
         for c in range(ncell):
             r = self.orc.run_model(kind, np.ascontiguousarray(params[:, c]), y0=None if y0 is None else y0[c],
-                                   timepoints=tp if timepoints else 500)
+                                   timepoints=tp if timepoints else 500, rates=want_rates)
             out["y_final"][c], out["phys_final"][c], out["flag"][c] = r["y_final"], r["phys_final"], r["flag"]
             out["stats"][c, self._iint] = r["stats"]["nintervals"]
             out["dissipation_time"][c] = r["dissipation_time"]
@@ -83,6 +86,8 @@ class _OracleBackedLibrary:
                 out["physics"][c, :n] = r["physics"]
             if want_chem:
                 out["abund"][c, :n] = r["abund"]
+            if want_rates:
+                out["rates"][c, :n] = r["rates"]
         return out
 
 
@@ -106,8 +111,23 @@ def test_model_disk_mode_host_logic(oracle, net, tmp_path, monkeypatch):
     _, data2 = datio.read_output_file(full)
     keep = np.array([n not in ("BULK", "SURFACE", "E-") for n in net.names])
     assert res2 == [0] and np.allclose(data2[0, 8:][keep], final[keep], rtol=1e-4, atol=1e-29)
+    # columnFile (format 8030, every writeStep-th output after the initial state) and rateFile (format 8021)
+    col, rat = tmp_path / "column.dat", tmp_path / "rates.dat"
+    res3 = model.cloud(param_dict={**pd_, "columnFile": str(col), "rateFile": str(rat), "writeStep": 2}, out_species=["OH", "CO"])
+    assert res3[0] == 0
+    lines = col.read_text().splitlines()
+    assert lines[0] == "Time,Density,gasTemp,dustTemp,av,radfield,zeta," + "OH".ljust(len(max(net.names, key=len))) + "," + "CO".ljust(len(max(net.names, key=len)))
+    nrows = phys.shape[0]
+    assert len(lines) - 1 == (nrows - 1) // 2
+    first = [float(datio._fix_exp(v)) for v in lines[1].split(",")]
+    assert len(first) == 9 and first[0] == pytest.approx(phys[2, 0, 0], rel=1e-3)
+    assert first[8] == pytest.approx(chem[2, 0, net.names.index("CO")], rel=1e-5)
+    rl = rat.read_text().splitlines()
+    assert len(rl) == nrows and len(rl[-1].split(",")) == 8 + net.nreac and "E-0" in rl[-1]
     with pytest.raises(NotImplementedError):
-        model.cloud(param_dict={**pd_, "columnFile": "c.dat"})
+        model.cloud(param_dict={**pd_, "fluxFile": "f.dat"})
+    with pytest.raises(ValueError, match="out_species"):
+        model.cloud(param_dict={**pd_, "columnFile": str(col)})
     with pytest.raises(RuntimeError, match="Offending keys"):
         model.cloud(param_dict={**pd_, "outputFile": str(full)}, return_array=True)
 

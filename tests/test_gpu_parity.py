@@ -330,3 +330,75 @@ def test_jshock_model_against_oracle(lib, oracle):
     res = model.jshock(10.0, param_dict={"initialDens": 1e3, "finalTime": 1.0, "reltol": 1e-6, "abstol_min": 1e-20},
                        return_array=True, starting_chemistry=sc)
     assert len(res) == 5 and res[-1] == 0
+
+
+def test_hot_core_g3_full_length_with_a_failed_dvode_call(lib):
+    """G3 at full length on the engine: hot_core(3, 300) from startcollapse, 1 Myr, all 282 stored times of the
+    reference's phase2-full.dat.  Run at reltol 1e-8 (no DVODE call fails on the engine) and at 1.03e-8, where one
+    call fails inside the mantle's evaporation and integrateODESystem's retry policy (chemistry.f90:246-292) takes
+    over: both must reproduce the reference's file (first seen on hardware: <= 5e-5 and 1.0e-3 dex)."""
+    gold = np.load(GOLDEN / "phase2_full.npz")
+    sc = np.load(GOLDEN / "startcollapse.npy")
+    rts = [1e-8, 1.03e-8]
+    p = params_from_dict({"endAtFinalDensity": False, "freefall": False, "initialDens": 1e5, "initialTemp": 10.0,
+                          "finalDens": 1e5, "finalTime": 1.0e6, "freezeFactor": 0.0, "thermdesorb": True, "temp_indx": 3,
+                          "max_temperature": 300.0, "reltol": rts})
+    y0 = np.repeat(np.append(sc, 1e5)[None, :], len(rts), axis=0)
+    out = lib.run_grid(1, p, y0=y0, timepoints=500, want_physics=True, want_chem=True)
+    assert (out["flag"] == 0).all() and (out["stats"][:, 7] == 282).all()
+    from uclchem_b200._capi import STAT_FIELDS
+    fails = out["stats"][:, STAT_FIELDS.index("nfailcall")]
+    assert fails[1] >= 1, fails        # the policy is exercised
+    for c in range(len(rts)):
+        np.testing.assert_allclose(out["physics"][c, 1:283, 2], gold["physics"][1:, 2], atol=6e-3)
+        worst = max(max_dex(out["abund"][c, row], gold["abund"][row]) for row in range(1, 283))
+        assert worst < DEX_TOL, (rts[c], worst)
+
+
+def test_cshock_through_three_dissipation_times(lib, oracle):
+    """C-shock past both cadence branches of cshock.f90:149-156 (steps of timestep_factor * t_diss up to 2 t_diss,
+    then x1.1) and through the peak of the ion-neutral drift velocity, at a shock speed above the 19 km/s
+    vaporisation threshold of sputtering.f90 (refractory ice species are sputtered too)."""
+    sc = np.load(GOLDEN / "shockstart.npy")
+    p = params_from_dict({"initialDens": 1e5, "initialTemp": 10.0, "finalTime": 1.0, "shock_vel": 30.0, "reltol": 1e-6,
+                          "abstol_min": 1e-20})
+    y0 = np.append(sc, 1e5)[None, :]
+    tdiss = lib.run_grid(2, p, y0=y0)["dissipation_time"][0]
+    p[PARAM_INDEX["finaltime"]] = 3.0 * tdiss
+    out = lib.run_grid(2, p, y0=y0, timepoints=600, want_physics=True, want_chem=True)
+    r = oracle.run_model(2, p[:, 0], y0=y0[0], timepoints=600)
+    n = r["physics"].shape[0]
+    assert out["flag"][0] == 0 and r["flag"] == 0 and out["stats"][0][7] == n - 1 and n > 205
+    t = out["physics"][0, :n, 0]
+    assert t[-1] > 3.0 * tdiss and np.isclose(t[-1] / t[-2], 1.1, rtol=1e-3) and np.isclose(t[100] - t[99], 0.01 * tdiss, rtol=1e-6)
+    np.testing.assert_allclose(out["physics"][0, :n, :4], r["physics"][:, :4], rtol=1e-6)
+    assert out["physics"][0, :n, 2].max() > 1000.0          # the gas was shock heated
+    worst = max(max_dex(out["abund"][0, row], r["abund"][row]) for row in range(1, n))
+    assert worst < DEX_TOL and max_dex(out["y_final"][0, :335], r["y_final"][:335]) < DEX_TOL, worst
+
+
+def test_rate_coefficient_overrides_against_oracle(lib, net):
+    """Per-reaction alpha / beta / gamma dictionaries of the reference's parameter dictionary (wrap.f90:744-761,
+    985-1019; keys are 1-based reaction indices of network.f90): the device uses an overridden copy of the three
+    tables; the oracle is handed a network whose arrays were edited the same way."""
+    import copy
+    from oracle.oracle import Oracle
+    from uclchem_b200._capi import UclgpuError
+    r_cr, r_two, r_frz = net.type_ranges["CRP"][0] + 3, net.type_ranges["TWOBODY"][0] + 40, net.type_ranges["FREEZE"][0] + 5
+    over = {"alpha": {r_cr + 1: 10.0 * net.alpha[r_cr], r_frz + 1: 0.1}, "beta": {r_two + 1: 0.5}, "gamma": {r_two + 1: 50.0}}
+    pd_ = {"initialDens": 1e5, "initialTemp": 20.0, "finalTime": 1e4, **over}
+    phys, chem, _, start, flag = model.cloud(param_dict=pd_, return_array=True)
+    net2 = copy.deepcopy(net)
+    net2.alpha[r_cr], net2.alpha[r_frz], net2.beta[r_two], net2.gama[r_two] = 10.0 * net.alpha[r_cr], 0.1, 0.5, 50.0
+    p = params_from_dict({k: v for k, v in pd_.items() if k not in over})
+    ref = Oracle(net2).run_model(0, p[:, 0])
+    base = Oracle(net).run_model(0, p[:, 0])
+    assert flag == 0 and ref["flag"] == 0
+    assert max_dex(start, ref["y_final"][:335]) < DEX_TOL
+    assert max_dex(start, base["y_final"][:335]) > 0.05                  # the overrides matter
+    # rates seen by the integrator carry the overrides (row 1 of the rate trajectory)
+    _, _, rates, _, _ = model.cloud(param_dict=dict(pd_, finalTime=1.0), return_array=True, return_rates=True)
+    assert rates[1, 0, r_cr] == pytest.approx(10.0 * net.alpha[r_cr] * 1.0, rel=1e-12)     # CRP: alpha * zeta
+    # gamma of a surface two-body reaction feeds tables fixed at generation time: refused, not half-applied
+    with pytest.raises(UclgpuError):
+        model.cloud(param_dict={"finalTime": 1.0, "gamma": {net.type_ranges["LH"][0] + 1: 10.0}}, return_array=True)

@@ -40,6 +40,7 @@ class UclgpuOpts(C.Structure):
     _fields_ = [("timepoints", C.c_int32), ("physics_traj", _pd), ("chem_traj", _pd), ("rates_traj", _pd),
                 ("dissipation_time", _pd), ("reserved0", C.c_int32), ("step_budget", C.c_int32),
                 ("cost_hint", _pd), ("y0_index", _pi), ("ny0", C.c_int64),
+                ("n_coeff", C.c_int64), ("coeff_which", _pi), ("coeff_index", _pi), ("coeff_value", _pd),
                 ("chunk_bytes", C.c_int64)]
 
 
@@ -113,7 +114,7 @@ class Library:
 
     def run_grid(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 0, want_physics=False,
                  want_chem=False, want_rates=False, step_budget: int = 0, cost_hint=None,
-                 chunk_bytes: int = 0, y0_index=None):
+                 chunk_bytes: int = 0, y0_index=None, coefficients=None):
         params = np.ascontiguousarray(params, np.float64)
         assert params.ndim == 2 and params.shape[0] == NPARAM
         ncell = params.shape[1]
@@ -137,6 +138,12 @@ class Library:
         opts.timepoints = timepoints
         opts.step_budget = step_budget
         opts.chunk_bytes = chunk_bytes
+        if coefficients:   # [(which, 0-based reaction, value), ...] with which in 0 alpha / 1 beta / 2 gamma
+            cw = np.ascontiguousarray([c[0] for c in coefficients], np.int32)
+            ci = np.ascontiguousarray([c[1] for c in coefficients], np.int32)
+            cv = np.ascontiguousarray([c[2] for c in coefficients], np.float64)
+            opts.n_coeff = len(cw)
+            opts.coeff_which, opts.coeff_index, opts.coeff_value = cw.ctypes.data_as(_pi), ci.ctypes.data_as(_pi), cv.ctypes.data_as(_pd)
         if cost_hint is not None:
             cost_hint = np.ascontiguousarray(cost_hint, np.float64)
             assert cost_hint.shape == (ncell,)

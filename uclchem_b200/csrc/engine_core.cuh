@@ -71,6 +71,9 @@ struct Scalars {
     // per-interval rate prefactors
     double k_desoh2, k_descr, k_deuvcr, stick_h, stick_h2, h2form_dust, scat_h2_pre, thermal_vel;
     int lh_on, swap_off, mxstep, kind;
+    // rate-coefficient tables in use: the compiled-in network.f90 arrays, or the caller's overridden copy
+    // (wrap.f90:744-761 alpha / beta / gamma dictionaries, uclgpu_opts.coeff_*)
+    const double *c_alpha, *c_beta, *c_gama;
     long long step_budget;
     // RHS ext quantities at the last evaluated state
     double e_sm, e_sb, e_blr, e_ism, e_tsw, e_dblr, e_dism, e_S;
@@ -439,9 +442,9 @@ __device__ __noinline__ double h2_form_efficiency_dev(double gastemp, double dus
 __device__ __forceinline__ double freeze_rate_dev(const Scalars &st, int r)
 {
     // freezeOutRate rates.f90:354-367
-    double fr = 1.0 + net_beta[r] * 16.71e-4 / (C_GRAIN_RADIUS * st.gastemp);
+    double fr = 1.0 + st.c_beta[r] * 16.71e-4 / (C_GRAIN_RADIUS * st.gastemp);
     if (st.p[UCL_P_FREEZEFACTOR] == 0.0 || st.dusttemp > C_MAX_GRAIN_TEMP) return 0.0;
-    return fr * st.p[UCL_P_FREEZEFACTOR] * net_alpha[r] * st.thermal_vel * sqrt(st.gastemp / net_mass1[r]) * C_GCS;
+    return fr * st.p[UCL_P_FREEZEFACTOR] * st.c_alpha[r] * st.thermal_vel * sqrt(st.gastemp / net_mass1[r]) * C_GCS;
 }
 
 __device__ __forceinline__ double diffusion_rate_dev(const Scalars &st, int r)
@@ -454,12 +457,12 @@ __device__ __forceinline__ double diffusion_rate_dev(const Scalars &st, int r)
     diffuse = diffuse + (v2 * exp(-0.5 * e2 / td));
     double desorb = v1 * exp(-e1 / td);
     desorb = desorb + v2 * exp(-e2 / td);
-    double reac = net_gama[r] / td;
+    double reac = st.c_gama[r] / td;
     double tunnel = net_tunnel[r];
     if (reac > tunnel) reac = tunnel;
     reac = fmax(v1, v2) * exp(-reac);
     reac = reac / (reac + desorb + diffuse);
-    return net_alpha[r] * reac * diffuse * NET_GDR / NET_NSITES;
+    return st.c_alpha[r] * reac * diffuse * NET_GDR / NET_NSITES;
 }
 
 __device__ __noinline__ void calc_rates(Smem &s)
@@ -501,7 +504,7 @@ __device__ __noinline__ void calc_rates(Smem &s)
     // ---- phase 1: unmasked rates ---------------------------------------------------------
     for (int r = tid; r < NREAC; r += NT) {
         double k = 0.0;
-        const double al = net_alpha[r], be = net_beta[r], ga = net_gama[r];
+        const double al = st.c_alpha[r], be = st.c_beta[r], ga = st.c_gama[r];
         switch (net_rtype[r]) {
         case 1: /* CRP :34-41 */
             k = (NET_CRP_LO != NET_CRP_HI) ? al * zeta : 0.0;
@@ -559,7 +562,7 @@ __device__ __noinline__ void calc_rates(Smem &s)
             if (NET_ER_LO != NET_ER_HI) {
                 int is_des = net_rtype[r] == 11;
                 int rl = is_des ? net_partner[r] : r;
-                double base = freeze_rate_dev(st, rl) * exp(-net_gama[rl] / dusttemp);
+                double base = freeze_rate_dev(st, rl) * exp(-st.c_gama[rl] / dusttemp);
                 int rd = is_des ? r : net_partner[r];
                 double des = net_desfrac[rd] * base;
                 if (net_phase[rd] == 2) des = 0.0;
@@ -631,7 +634,7 @@ __device__ __noinline__ void calc_rates(Smem &s)
 #if NET_NGAR > 0
         if (ty == 21 && NET_GAR_LO != NET_GAR_HI) {
             const double *g = net_gar_params + 7 * (r - NET_GAR_LO);
-            k = (double)0.6f * net_alpha[r] * g[0] /
+            k = (double)0.6f * st.c_alpha[r] * g[0] /
                 ((double)1.f + g[1] * pow(phi_new, g[2]) *
                                    ((double)1.f + g[3] * pow(gastemp, g[4]) * pow(phi_new, -g[5] - g[6] * log(gastemp))));
         }
@@ -641,7 +644,7 @@ __device__ __noinline__ void calc_rates(Smem &s)
         if (r == NET_NR_H2_HV) k = st.scat_h2_pre * h2_self_shielding_dev(st.h2col);
         if (r == NET_NR_CO_HV) k = co_photo_rate_dev(st.h2col, st.cocol, radfield, av);
         if (r == NET_NR_C_HV)
-            k = c_ionization_rate_dev(net_alpha[r], net_gama[r], gastemp, st.ccol, st.h2col, av, radfield);
+            k = c_ionization_rate_dev(st.c_alpha[r], st.c_gama[r], gastemp, st.ccol, st.h2col, av, radfield);
         s.rate[r] = k;
     }
     BLOCK_SYNC();

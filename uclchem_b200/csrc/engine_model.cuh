@@ -34,6 +34,7 @@ struct RunArgs {
     int trace_cap, dump_at;
     int warm_restart;            // experimental (UCLGPU_WARM=1): keep the BDF history across output times
     long long max_steps;         // uclgpu_opts.step_budget: abandon a cell (flag -5) beyond this many BDF steps; 0 = off
+    const double *coef;          // [3][NREAC] overridden alpha / beta / gamma tables, or null
     const int *order;            // processing order of the cells (most expensive first) or null
     double *dump;
 };
@@ -564,6 +565,9 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
     st.abstol_factor = st.p[UCL_P_ABSTOL_FACTOR];
     st.mxstep = (int)st.p[UCL_P_MXSTEP];
     st.step_budget = a.max_steps;
+    st.c_alpha = a.coef ? a.coef : net_alpha;
+    st.c_beta = a.coef ? a.coef + NREAC : net_beta;
+    st.c_gama = a.coef ? a.coef + 2 * NREAC : net_gama;
     st.rtol = st.p[UCL_P_RELTOL];
     st.last_temp = 99.0e99;
     st.nst = st.nfe = st.nje = st.nlu = st.nni = st.ncfn = st.netf = st.nintervals = 0;

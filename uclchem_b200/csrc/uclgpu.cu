@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         st.hist_valid = 0;
         st.use_tcrit = 0;
         st.step_budget = 0;
+        st.c_alpha = net_alpha; st.c_beta = net_beta; st.c_gama = net_gama;
         st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = st.cyc_total = 0;
         initialize_physics_dev(st);
         T0_END
@@ -454,6 +455,7 @@ extern "C" int uclgpu_last_kernel_ms(int dev, double *ms, int64_t *launches)
 // D2H copy per array brings back exactly this chunk's rows and the host scatters them into the caller's arrays.
 struct DevBuf {
     int *y0_index = nullptr;
+    double *coef = nullptr;
     double *params = nullptr, *y0 = nullptr, *y_final = nullptr, *phys = nullptr, *ptraj = nullptr, *ctraj = nullptr,
            *rtraj = nullptr, *tdiss = nullptr;
     int32_t *flag = nullptr;
@@ -471,8 +473,8 @@ struct DevBuf {
     void release()
     {
         release_chunk();
-        cudaFree(params); cudaFree(y0); cudaFree(y0_index);
-        params = y0 = nullptr; y0_index = nullptr;
+        cudaFree(params); cudaFree(y0); cudaFree(y0_index); cudaFree(coef);
+        params = y0 = nullptr; y0_index = nullptr; coef = nullptr;
     }
 };
 
@@ -501,6 +503,30 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
         for (int64_t c = 0; c < ncell; c++)
             if (y0_index[c] < 0 || y0_index[c] >= opts->ny0) return UCLGPU_ERR_BAD_ARGUMENT;
     }
+    // per-reaction alpha / beta / gamma overrides (wrap.f90:744-761,985-1019): one overridden copy of the three
+    // tables per call, the same for every cell.  gamma of a surface two-body reaction also enters tables that are
+    // precomputed at generation time (tunnelling probability, desorption fraction): refused, not half-applied.
+    std::vector<double> coef;
+    if (opts && opts->n_coeff > 0) {
+        if (!opts->coeff_which || !opts->coeff_index || !opts->coeff_value) return UCLGPU_ERR_BAD_ARGUMENT;
+        coef.resize(3 * (size_t)NREAC);
+        CK(cudaSetDevice(g_dev[0].id));
+        CK(cudaMemcpyFromSymbol(coef.data(), net_alpha, sizeof(double) * NREAC));
+        CK(cudaMemcpyFromSymbol(coef.data() + NREAC, net_beta, sizeof(double) * NREAC));
+        CK(cudaMemcpyFromSymbol(coef.data() + 2 * NREAC, net_gama, sizeof(double) * NREAC));
+        std::vector<unsigned char> rtype(NREAC);
+        CK(cudaMemcpyFromSymbol(rtype.data(), net_rtype, NREAC));
+        for (int64_t k = 0; k < opts->n_coeff; k++) {
+            const int w = opts->coeff_which[k], r = opts->coeff_index[k];
+            if (w < 0 || w > 2 || r < 0 || r >= NREAC) return UCLGPU_ERR_BAD_ARGUMENT;
+            const int ty = rtype[r];
+            if (w == 2 && (ty == 12 || ty == 13 || ty == 10 || ty == 11)) {
+                snprintf(g_err, sizeof(g_err), "gamma override of surface reaction %d is not supported (tabulated tunnelling / desorption fraction)", r + 1);
+                return UCLGPU_ERR_BAD_ARGUMENT;
+            }
+            coef[(size_t)w * NREAC + r] = opts->coeff_value[k];
+        }
+    }
     const std::vector<int> ord = cost_order(params, ncell, opts ? opts->cost_hint : nullptr);
     // bytes of COMPACT result storage per cell on the device
     const size_t per_cell = sizeof(double) * (NEQ + UCLGPU_NPHYS + 1) + sizeof(int32_t) + sizeof(int) + sizeof(uclgpu_stats) +
@@ -527,6 +553,10 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
                     CK(cudaMalloc(&B.y0_index, sizeof(int) * ncell));
                     CK(cudaMemcpyAsync(B.y0_index, y0_index, sizeof(int) * ncell, cudaMemcpyHostToDevice, d.stream));
                 }
+            }
+            if (!coef.empty()) {
+                CK(cudaMalloc(&B.coef, sizeof(double) * coef.size()));
+                CK(cudaMemcpyAsync(B.coef, coef.data(), sizeof(double) * coef.size(), cudaMemcpyHostToDevice, d.stream));
             }
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -560,7 +590,7 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
                 RunArgs a;
                 memset(&a, 0, sizeof(a));
                 a.kind = (int)kind; a.ncell = ncell; a.nrun = (long long)n; a.compact = 1; a.order = B.order;
-                a.params = B.params; a.y0 = B.y0; a.y0_index = B.y0_index; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
+                a.params = B.params; a.y0 = B.y0; a.y0_index = B.y0_index; a.coef = B.coef; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
                 if (opts) {
                     a.max_steps = opts->step_budget;
                     a.timepoints = opts->timepoints;

@@ -4,6 +4,10 @@
                            time ``io.f90:80-83`` (format 8020)
 ``write_abundances``    -- ``abundSaveFile``: one line of final abundances, ``io.f90:48-56`` (format 8010)
 ``read_abundances``     -- ``abundLoadFile``: list-directed read of that line, ``io.f90:36-46``
+``write_column_output`` -- ``columnFile``: header ``io.f90:23-24`` (format 333), selected species every
+                           ``writeStep``-th output ``io.f90:108-118`` (format 8030)
+``write_rate_output``   -- ``rateFile``: no header, physics + every rate coefficient per output time
+                           ``io.f90:94-97`` (format 8021, three-digit exponents)
 ``read_output_file``    -- what ``uclchem.analysis.read_output_file`` returns for a full output file
 
 The rows carry six significant digits like the reference's (``1pe15.5``); Fortran writes a
@@ -46,6 +50,44 @@ def write_full_output(path, species, physics, abund) -> None:
     """physics [nrows, 8], abund [nrows, nspec] (the trimmed trajectory of one model, point = 1)."""
     lines = [PHYSICS_HEADER + _species_header(species)]
     lines += [format_row(p, a) for p, a in zip(np.asarray(physics), np.asarray(abund))]
+    Path(path).write_text("\n".join(lines) + "\n")
+
+
+def _e3(x: float, width: int, digits: int) -> str:
+    """Fortran ``1pe<width>.<digits>e3``: always a three-digit exponent with the ``E``."""
+    mant, exp = f"{x:.{digits}E}".split("E")
+    e = int(exp)
+    return f"{mant}E{'+' if e >= 0 else '-'}{abs(e):03d}".rjust(width)
+
+
+def _physics7(physics_row) -> str:
+    t, dens, tg, td, av, rad, zeta = physics_row[:7]
+    return (f"{_e(t, 11, 3)},{_e(dens, 11, 4)},{tg:8.2f},{td:8.2f},{_e(av, 11, 4)},{_e(rad, 11, 4)},"
+            f"{_e(zeta, 11, 4)},")
+
+
+def write_column_output(path, species, out_species, physics, abund, write_step: int = 1) -> None:
+    """columnFile: the species of `out_species` every `write_step`-th output.  The reference's counter starts at
+    zero (chemistry.f90:28) and is compared before it is advanced (io.f90:110-117), so the initial state is not
+    written and, with writeStep = 1, every later row is."""
+    species = list(species)
+    idx = [species.index(sp) for sp in out_species]
+    w = max(len(sp) for sp in species)
+    lines = ["Time,Density,gasTemp,dustTemp,av,radfield,zeta," + ",".join(sp.ljust(w) for sp in out_species)]
+    counter = 0
+    for p_, a_ in zip(np.asarray(physics), np.asarray(abund)):
+        if counter == write_step:
+            counter = 1
+            lines.append(_physics7(p_) + ",".join(_e(a_[i], 15, 5) for i in idx))
+        else:
+            counter += 1
+    Path(path).write_text("\n".join(lines) + "\n")
+
+
+def write_rate_output(path, physics, rates) -> None:
+    """rateFile: one row per output time, physics columns then every rate coefficient (format 8021)."""
+    lines = [_physics7(p_) + f"{int(p_[7]):4d}," + ",".join(_e3(v, 15, 5) for v in r_)
+             for p_, r_ in zip(np.asarray(physics), np.asarray(rates))]
     Path(path).write_text("\n".join(lines) + "\n")
 
 

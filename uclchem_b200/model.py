@@ -11,8 +11,8 @@ Differences from the reference, all deliberate:
 
 * file based I/O is done on the host after the run (``datio.py``): ``outputFile`` (full output,
   ``io.f90`` formats 335/8020), ``abundSaveFile`` / ``abundLoadFile`` (format 8010) are honoured in the
-  reference's disk mode (neither ``return_array`` nor ``return_dataframe``); ``columnFile``,
-  ``rateFile`` and ``fluxFile`` are not written; combining file keys with the in-memory modes is
+  reference's disk mode (neither ``return_array`` nor ``return_dataframe``), as are ``columnFile`` (+ ``writeStep``)
+  and ``rateFile``; ``fluxFile`` is not written; combining file keys with the in-memory modes is
   refused with the reference's own error (``model.py:121-131``);
 * parameters start from ``defaultparameters.f90`` on every call (the reference leaks
   parameters between calls, SURVEY.md Q6);
@@ -58,6 +58,21 @@ def pre_flight_checklist(return_array, return_dataframe, return_rates, starting_
                 "return_rates and return_heating can only be used with return_array or return_dataframe set to True; ")
 
 
+def _coefficients(pd_):
+    """The reference's per-reaction overrides (wrap.f90:744-761): `alpha`, `beta`, `gamma` entries of the parameter
+    dictionary are {reaction index (1-based, as in network.f90): value} dictionaries.  Returned as the C ABI's
+    (which, 0-based reaction, value) triples; the keys are removed from `pd_`."""
+    out = []
+    for which, key in enumerate(("alpha", "beta", "gamma")):
+        d = pd_.pop(key, None)
+        if d is None:
+            continue
+        if not isinstance(d, dict):
+            raise ValueError(f"{key} must be a dictionary of reaction index: value pairs")
+        out += [(which, int(k) - 1, float(v)) for k, v in d.items()]
+    return out
+
+
 def _format_output(n_out, abunds, success_flag):
     """model.py:76-81"""
     abunds = [] if (success_flag < 0 or n_out == 0) else list(abunds[:n_out])
@@ -72,10 +87,14 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
     pre_flight_checklist(return_array, return_dataframe, return_rates, starting_chemistry, pd_)
     # disk mode of the reference: files named in the dictionary are read before / written after the run
     files = {k: pd_.pop(k) for k in list(pd_) if k.endswith("file")}
-    for k in ("columnfile", "ratefile", "fluxfile"):
-        if k in files:
-            raise NotImplementedError(f"{k} is not written by the GPU path; use return_array / return_dataframe")
+    if "fluxfile" in files:   # REACTIONRATE is only filled by networks built with MakeRates' enable_rates_to_disk
+        raise NotImplementedError("fluxFile is not written by the GPU path; use return_rates and "
+                                  "uclchem_b200.analysis.rates_to_dy_and_flux")
+    if "columnfile" in files and not out_species:
+        raise ValueError("columnFile needs out_species (the reference writes the species of outSpecies)")
+    write_step = int(pd_.pop("writestep", 1))
     pd_.update(extra)
+    coefficients = _coefficients(pd_)
     try:
         params = params_from_dict(pd_, ncell=1)
     except KeyError as e:
@@ -91,21 +110,28 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
     elif "abundloadfile" in files:          # readInputAbunds, io.f90:36-46
         y0 = np.zeros((1, lib.neq))
         y0[0, : lib.nspec] = datio.read_abundances(files["abundloadfile"], lib.nspec)
-    want_rows = traj or "outputfile" in files
+    want_rows = traj or any(k in files for k in ("outputfile", "columnfile", "ratefile"))
+    want_rates = (traj and return_rates) or "ratefile" in files
     out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if want_rows else 0,
-                       want_physics=want_rows, want_chem=want_rows, want_rates=traj and return_rates)
+                       want_physics=want_rows, want_chem=want_rows, want_rates=want_rates, coefficients=coefficients)
     while not traj and want_rows and int(out["flag"][0]) == -6 and timepoints < (1 << 20):
         # disk mode has no row limit in the reference (rows go straight to the file, io.f90:59-83): the rows come
         # back through the in-memory buffers here, so a model with more output intervals is re-run with more room
         timepoints *= 4
-        out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints, want_physics=True, want_chem=True)
+        out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints, want_physics=True, want_chem=True,
+                           want_rates=want_rates, coefficients=coefficients)
     flag = int(out["flag"][0])
     tdiss = float(out["dissipation_time"][0]) if flag >= 0 else None   # model.py:606-607
     if not traj:
+        nrows = min(int(out["stats"][0][7]) + 1, timepoints + 1)
         if "outputfile" in files:
-            nrows = min(int(out["stats"][0][7]) + 1, timepoints + 1)
             datio.write_full_output(files["outputfile"], lib.species, out["physics"][0, :nrows],
                                     out["abund"][0, :nrows])
+        if "columnfile" in files:
+            datio.write_column_output(files["columnfile"], lib.species, out_species, out["physics"][0, :nrows],
+                                      out["abund"][0, :nrows], write_step)
+        if "ratefile" in files:
+            datio.write_rate_output(files["ratefile"], out["physics"][0, :nrows], out["rates"][0, :nrows])
         if "abundsavefile" in files:          # finalOutput, io.f90:48-56
             datio.write_abundances(files["abundsavefile"], out["y_final"][0, : lib.nspec])
         n_out = len(out_species) if out_species else 0
@@ -209,6 +235,7 @@ def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None, ret
         raise RuntimeError("file output is per model; use return_array=True for grids.\n"
                            f"Offending keys: {', '.join(file_keys)}")
     pd_.update(extra)
+    coefficients = _coefficients(pd_)   # one set of overrides for the whole grid
     params = params_from_dict(pd_)
     ncell = params.shape[1]
     y0 = None
@@ -219,7 +246,8 @@ def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None, ret
         y0 = np.zeros((ncell, lib.neq))
         y0[:, : lib.nspec] = sc[:, : lib.nspec]
     out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if return_array else 0,
-                       want_physics=return_array, want_chem=return_array, want_rates=return_array and return_rates)
+                       want_physics=return_array, want_chem=return_array, want_rates=return_array and return_rates,
+                       coefficients=coefficients)
     res = {"flag": out["flag"], "abundances": out["y_final"][:, : lib.nspec], "physics": out["phys_final"],
            "stats": out["stats"], "species": lib.species}
     if return_array:
