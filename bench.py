@@ -257,6 +257,9 @@ class StepSpec:
 
 
 class Workload:
+    def cost_hint(self, k, attempts):
+        return None
+
     tag = "default"
     nslice = NSLICE
     step_budget = STEP_BUDGET  # BDF steps per model before it is abandoned: ~10x a typical model of the workload
@@ -301,6 +304,22 @@ class Config2(Workload):
 
     def step(self, k):
         return StepSpec(0, self.params[:, self.slices[k % NSLICE]])
+
+    def cost_hint(self, k, attempts):
+        """Expected cost of the cells of step k from what is already known about the grid: `attempts` holds, per
+        flat grid index, the BDF step attempts of the cells integrated so far (NaN = not yet).  A cell's zeta
+        neighbours (flat index -1 / +1: same density and temperature) belong to the previous / next slice, so from the
+        second step on every cell has a measured neighbour; cells without one get the median.  This is what a
+        user sweeping a grid plane by plane can do with `uclgpu_opts.cost_hint`; the first step runs without."""
+        idx = self.slices[k % NSLICE]
+        n = len(attempts)
+        h = np.where(np.isnan(attempts[idx]), np.nan, attempts[idx])          # a previous visit of the same cell
+        for d in (-1, 1, -2, 2):
+            nb = np.clip(idx + d, 0, n - 1)
+            h = np.where(np.isnan(h), attempts[nb], h)
+        if np.isnan(h).all():
+            return None
+        return np.where(np.isnan(h), np.nanmedian(h), h)
 
 
 class Config3(Workload):
@@ -401,6 +420,8 @@ def main():
                     help="BDF steps after which a cell is abandoned (flag -5, not counted); 0 = the reference's unbounded crawl; "
                          "default: the workload's own (about ten times what a typical model of the workload needs)")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="bound of the cpu_baseline sample")
+    ap.add_argument("--no-cost-hint", action="store_true",
+                    help="do not pass uclgpu_opts.cost_hint (measured step counts of the neighbouring zeta plane, workload 2)")
     ap.add_argument("--cells", type=int, default=0, help="debug: override the grid size (not a valid bench line)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -472,9 +493,12 @@ def main():
             self.stats = torch.zeros((self.n, nstat), dtype=torch.int64).pin_memory()
             self.y0_index = None if y0_index is None else torch.from_numpy(np.ascontiguousarray(y0_index, np.int32)).pin_memory()
 
-        def run(self, budget, y0_table=None):
+        def run(self, budget, y0_table=None, cost_hint=None):
             opts = UclgpuOpts()
             opts.step_budget = budget
+            if cost_hint is not None:
+                self._hint = np.ascontiguousarray(cost_hint, np.float64)
+                opts.cost_hint = C.cast(self._hint.ctypes.data, pd_)
             y0p = None
             if y0_table is not None:
                 opts.y0_index = C.cast(self.y0_index.data_ptr(), pi_)
@@ -502,12 +526,12 @@ def main():
             self.main = Batch(spec.kind, spec.params, spec.y0_index)
             self.n = self.main.n
 
-        def run(self, budget):
+        def run(self, budget, cost_hint=None):
             ms = nl = 0.0
             if self.s1 is not None:
                 m1, n1 = self.s1.run(budget)
                 ms, nl = ms + m1, nl + n1
-            m2, n2 = self.main.run(budget, None if self.s1 is None else self.s1.y)
+            m2, n2 = self.main.run(budget, None if self.s1 is None else self.s1.y, cost_hint)
             return ms + m2, int(nl + n2)
 
         def all_stats(self):
@@ -551,12 +575,19 @@ def main():
     kernel_ms, launches = 0.0, 0
     n_ok = n_budget = n_cells = 0
     step_stats = []
+    attempts = np.full(getattr(wl, "params", np.zeros((1, 0))).shape[1], np.nan)   # per grid cell, for the cost hint
+    i_att = [STAT_FIELDS.index(f) for f in ("nst", "netf", "ncfn")]
+    hinted_steps = 0
     with ClockSampler(local_rank) as clk:
         barrier()
         t0 = time.perf_counter()
         for k in range(a.steps):
             b = steps[step_id(k) % wl.nslice]
-            ms, nl = b.run(a.step_budget)
+            hint = wl.cost_hint(step_id(k), attempts) if not a.no_cost_hint else None
+            hinted_steps += hint is not None
+            ms, nl = b.run(a.step_budget, hint)
+            if len(attempts):
+                attempts[wl.slices[step_id(k) % NSLICE]] = b.main.stats.numpy()[:, i_att].sum(axis=1)
             kernel_ms += ms
             launches += nl
             if world > 1:
@@ -631,6 +662,9 @@ def main():
                              h2d_bytes=first.h2d_bytes(), d2h_bytes=first.d2h_bytes(), cpu=cpu, parity=parity,
                              traffic=traffic, stat_fields=STAT_FIELDS, per_rank_kernel_ms=per_rank,
                              gather_bytes=(world - 1) * n_max * (neq + 1) * 8 if world > 1 else 0)
+        line["config"]["cost_hint"] = (f"{hinted_steps} of {a.steps} steps ran with uclgpu_opts.cost_hint = step attempts measured on the "
+                                       "neighbouring zeta plane in an earlier step of this run (the first step has none)"
+                                       if hinted_steps else "none (generic longest-first order)")
         if a.workload == 1:
             line["single_model_seconds"] = kernel_ms / 1e3 / a.steps
         print(json.dumps(line), flush=True)

@@ -204,3 +204,18 @@ def test_deferred_photo_reactions(gen, net):
         rows = gen.deferred_rows[r]
         assert 1 <= len(rows) <= 4 and sum(sg for _, sg in rows) == 1   # A -> B + C
         assert all(i < net.nspec and net.names[i][0] not in "#@" for i, _ in rows)
+
+
+def test_unsupported_networks_are_refused_by_the_generator(net):
+    """Two-phase networks and refractory lists have reference code paths the engine does not implement
+    (hotcore.f90:92-107, rates.f90:217, surfacereactions.f90:112, chemistry.f90:198): generation refuses them."""
+    import copy
+    from uclchem_b200.makerates_cuda import Generated
+    two = copy.copy(net)
+    two.three_phase = False
+    with pytest.raises(NotImplementedError, match="two-phase"):
+        Generated(two)
+    refr = copy.copy(net)
+    refr.refractory_list = np.array([200], dtype=np.int64)
+    with pytest.raises(NotImplementedError, match="refractory"):
+        Generated(refr)

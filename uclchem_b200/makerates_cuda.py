@@ -104,6 +104,14 @@ class Generated:
     """All tables of one network, in memory (also used by the CPU tests)."""
 
     def __init__(self, net: Network, dense_threshold: float = 0.9, factor_terms_per_lane: int = 8):
+        # refused, not ignored (DESIGN.md section 0): the engine implements the three-phase paths only -- the
+        # two-phase branches of hotcore.f90:92-107 (instant sublimation / thermal evaporation), rates.f90:217 and
+        # surfacereactions.f90:112 are not built -- and not the refractory subtraction of chemistry.f90:198
+        if not net.three_phase:
+            raise NotImplementedError("two-phase networks (THREE_PHASE = .False.) are not supported by the CUDA back-end")
+        if len(net.refractory_list):
+            raise NotImplementedError("networks with refractory species (refractoryList) are not supported by the CUDA "
+                                      "back-end: safeBulk of chemistry.f90:198 is not implemented on the device")
         self.net = net
         self.sym = sym = symbolic.build(net, dense_threshold)
         neq = sym.neq
