@@ -179,7 +179,7 @@ def run_oracle_sample(params, cores, seconds, cells=None, kind=0, y0=None, tag="
     n_fin = int(fin.sum())
     rate = cores * n_fin / core_s if core_s > 0 else 0.0
     nst = st[:, 0].astype(np.float64)
-    return {"rate": rate, "wall": wall, "cells": order, "y": y, "flag": flag, "finished": fin, "n_finished": n_fin,
+    return {"rate": rate, "wall": wall, "cells": order, "y": y, "flag": flag, "finished": fin, "n_finished": n_fin, "stats": st,
             "n_cut": int(cut.sum()), "core_seconds": core_s,
             "ms_per_bdf_step": 1e3 * core_s / nst[fin].sum() if n_fin else None,
             "steps_per_model": float(nst[fin].mean()) if n_fin else None,
@@ -647,6 +647,21 @@ def main():
                 yr, yg = r["y"][ok][:, :335], y_gpu[cells[ok]][:, :335]
                 m = yr > 1e-15
                 dex = np.abs(np.log10(np.where(m, yg / np.where(m, yr, 1.0), 1.0)))
+                if ok.any():
+                    # the worst cell with what each arm did on it: a cell on which either arm had failed DVODE calls
+                    # re-evaluated its interval-frozen rates mid-interval, so the two arms are
+                    # no longer integrating the same piecewise problem there
+                    kk = np.where(ok)[0][int(dex.max(axis=1).argmax())]
+                    gs = dict(zip(STAT_FIELDS, b.main.stats.numpy()[cells[kk]].tolist()))
+                    pidx = {k_: i_ for i_, k_ in enumerate(("initialtemp", "initialdens"))}
+                    parity["worst_cell"] = {"dex": float(dex.max()), "cell_in_step": int(cells[kk]),
+                                            "initialTemp": float(b.spec.params[0, cells[kk]]), "initialDens": float(b.spec.params[1, cells[kk]]),
+                                            "gpu_steps": gs["nst"], "gpu_failed_dvode_calls": gs["nfailcall"], "gpu_error_test_failures": gs["netf"],
+                                            "oracle_steps": int(r["stats"][kk, 0]), "oracle_convergence_failures": int(r["stats"][kk, 5])}
+                    nf = b.main.stats.numpy()[cells[ok]][:, STAT_FIELDS.index("nfailcall")]
+                    clean = nf == 0
+                    parity["max_dex_on_cells_without_failed_gpu_calls"] = float(dex[clean].max()) if clean.any() else None
+                    parity["cells_with_failed_gpu_calls_in_sample"] = int((~clean).sum())
                 parity.update({"max_dex_vs_oracle_on_sample": float(dex.max()) if ok.any() else None,
                                "cells_above_0.01_dex": int((dex.max(axis=1) > 0.01).sum()) if ok.any() else None,
                                "sample_cells_compared": int(ok.sum()),

@@ -200,8 +200,11 @@ class Oracle:
                                out.ctypes.data_as(_pd))
         return out
 
-    def run_model(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 500, rates: bool = False):
-        """Returns dict(flag, y_final, phys_final, physics[nrows,8], abund[nrows,nspec], rates, stats, t_diss)."""
+    def run_model(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 500, rates: bool = False,
+                  pp_grid=None, pp_coldens: bool = False):
+        """Returns dict(flag, y_final, phys_final, physics[nrows,8], abund[nrows,nspec], rates, stats, t_diss).
+        kind 5 (postprocess) takes the tracer history pp_grid [10, ntime] (time in s, density, gas T, dust T,
+        radfield, zeta, N_H, N_H2, N_CO, N_C; the columns are only read with pp_coldens)."""
         net = self.net
         params = np.ascontiguousarray(params, np.float64)
         assert params.shape == (NPARAM,)
@@ -217,10 +220,17 @@ class Oracle:
         if y0 is not None:
             y0 = np.ascontiguousarray(y0, np.float64)
             y0p = y0.ctypes.data_as(_pd)
-        flag = self.lib.orc_run_model(
+        ntime, gp = 0, None
+        if pp_grid is not None:
+            pp_grid = np.ascontiguousarray(pp_grid, np.float64)
+            assert pp_grid.ndim == 2 and pp_grid.shape[0] == 10
+            ntime, gp = pp_grid.shape[1], pp_grid.ctypes.data_as(_pd)
+        self.lib.orc_run_model_pp.restype = C.c_int
+        flag = self.lib.orc_run_model_pp(
             C.byref(self._c), C.c_int(kind), params.ctypes.data_as(_pd), y0p, yfin.ctypes.data_as(_pd),
             pfin.ctypes.data_as(_pd), C.c_int(timepoints), phys.ctypes.data_as(_pd), chem.ctypes.data_as(_pd),
-            rts.ctypes.data_as(_pd) if rates else None, C.byref(nrows), C.byref(tdiss), C.byref(st))
+            rts.ctypes.data_as(_pd) if rates else None, C.byref(nrows), C.byref(tdiss), C.byref(st),
+            C.c_int(ntime), gp, C.c_int(1 if pp_coldens else 0))
         n = nrows.value
         return dict(flag=flag, y_final=yfin, phys_final=pfin, physics=phys[:n], abund=chem[:n],
                     rates=rts[:n] if rates else None,

@@ -759,10 +759,12 @@ void orc_rhs(void *ctx, double t, const double *y, double *ydot)
     double d = y[neq - 1];
     for (int i = 0; i < neq; i++) ydot[i] = 0.0;
     /* points = 1: cloudSize/real(points) = cloudSize; *ColToCell = 0 */
-    m->cocol = 0.0 + 0.5 * y[net->named[I_NCO]] * d * (m->cloudsize / (double)1.0f);
-    m->h2col = 0.0 + 0.5 * y[net->named[I_NH2]] * d * (m->cloudsize / (double)1.0f);
-    m->rate[net->named[R_H2_HV]] = orc_h2_photo_diss_rate(m->h2col, m->radfield, m->av, 1.0);
-    m->rate[net->named[R_CO_HV]] = orc_co_photo_diss_rate(m->h2col, m->cocol, m->radfield, m->av);
+    if (!m->pp_coldens) { /* chemistry.f90:310-319: column densities are fixed for postprocessing data */
+        m->cocol = 0.0 + 0.5 * y[net->named[I_NCO]] * d * (m->cloudsize / (double)1.0f);
+        m->h2col = 0.0 + 0.5 * y[net->named[I_NH2]] * d * (m->cloudsize / (double)1.0f);
+        m->rate[net->named[R_H2_HV]] = orc_h2_photo_diss_rate(m->h2col, m->radfield, m->av, 1.0);
+        m->rate[net->named[R_CO_HV]] = orc_co_photo_diss_rate(m->h2col, m->cocol, m->radfield, m->av);
+    }
     m->safe_mantle = fmax(1e-30, y[net->named[I_NSURFACE]]);
     m->safe_bulk = fmax(1e-30, y[net->named[I_NBULK]]);
     m->blr = fmin(1.0, orc_num_sites_per_grain() / (orc_gas_dust_density_ratio() * m->safe_bulk));

@@ -34,6 +34,10 @@ typedef struct orc_model {
         cs_dissipation_time, cs_max_temp, cs_drift_vel, cs_zn, cs_vn, cs_tn, cs_ts, cs_initial_dens_cs,
         cs_grain_number_density, cs_grain_radius_cgs;
     int cs_coflag;
+    /* postprocess.f90 module state: tracer history [10][pp_ntime] = time (s), density, gas T, dust T, radfield,
+     * zeta, N_H, N_H2, N_CO, N_C; the last four only with pp_coldens */
+    int pp_ntime, pp_coldens, pp_tstep;
+    const double *pp_grid;
     /* jshock.f90 module state */
     double js_max_temp, js_vmin, js_tshock, js_tcool, js_max_dens, js_t_lambda, js_n_lambda, js_v0;
     /* collapse.f90 module state */

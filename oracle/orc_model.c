@@ -116,6 +116,27 @@ static int model_initialize_physics(orc_model *m)
         return orc_collapse_initialize(m);
     case UCLGPU_JSHOCK:
         return orc_jshock_initialize(m);
+    case UCLGPU_POSTPROCESS: { /* postprocess.f90:24-92 */
+        if (!m->pp_grid || m->pp_ntime < 1) return -1;
+        const double *g = m->pp_grid;
+        const int n = m->pp_ntime;
+        if (m->pp_coldens) m->cloudsize = (double)0.f; /* shielding column densities supplied separately */
+        m->p[UCL_P_ENDATFINALDENSITY] = 0.0;
+        m->p[UCL_P_FREEFALL] = 0.0;
+        m->pp_tstep = 1;
+        m->target_time = g[0];
+        m->density = g[1 * n];
+        m->gastemp = g[2 * n];
+        m->dusttemp = g[3 * n];
+        m->radfield = g[4 * n];
+        m->zeta = g[5 * n];
+        if (m->pp_coldens) {
+            m->coldens = g[6 * n];
+            m->av = (double)5.348e-22f * m->coldens;
+        }
+        m->p[UCL_P_FINALTIME] = g[n - 1] / SECONDS_PER_YEAR;
+        return 0;
+    }
     }
     return -1;
 }
@@ -161,6 +182,10 @@ static void update_target_time(orc_model *m)
     case UCLGPU_JSHOCK:
         orc_jshock_update_target_time(m);
         break;
+    case UCLGPU_POSTPROCESS: /* postprocess.f90:100-106 (tstep past the end of the history: clamped, see run loop) */
+        if (m->pp_tstep > m->pp_ntime) m->pp_tstep = m->pp_ntime; /* guard: the Fortran would read past the array */
+        m->target_time = m->pp_grid[m->pp_tstep - 1] + (double)1.f * SECONDS_PER_YEAR;
+        break;
     }
 }
 
@@ -190,6 +215,22 @@ static void model_update_physics(orc_model *m)
     case UCLGPU_JSHOCK:
         orc_jshock_update_physics(m);
         break;
+    case UCLGPU_POSTPROCESS: { /* postprocess.f90:112-129 */
+        const double *g = m->pp_grid;
+        const int n = m->pp_ntime, k = m->pp_tstep - 1;
+        m->target_time = g[k];
+        m->density = g[1 * n + k];
+        m->gastemp = g[2 * n + k];
+        m->dusttemp = g[3 * n + k];
+        m->radfield = g[4 * n + k];
+        m->zeta = g[5 * n + k];
+        if (m->pp_coldens) {
+            m->coldens = g[6 * n + k];
+            m->av = (double)5.348e-22f * m->coldens;
+        }
+        m->pp_tstep = m->pp_tstep + 1;
+        break;
+    }
     }
 }
 
@@ -310,6 +351,12 @@ static void chemistry_setup(orc_model *m)
     m->h2col = 0.0 + (double)0.5f * a[nm[I_NH2]] * m->density * cs;
     m->cocol = 0.0 + (double)0.5f * a[nm[I_NCO]] * m->density * cs;
     m->ccol = 0.0 + (double)0.5f * a[nm[I_NC]] * m->density * cs;
+    if (m->pp_coldens) { /* chemistry.f90:183-189: postprocessed tracers have column densities provided */
+        const int n = m->pp_ntime, k = m->pp_tstep - 1;
+        m->h2col = m->pp_grid[7 * n + k];
+        m->cocol = m->pp_grid[8 * n + k];
+        m->ccol = m->pp_grid[6 * n + k] * a[nm[I_NC]];
+    }
     double sb = 0.0, ss = 0.0;
     for (int k = 0; k < net->nsurf; k++) sb += a[net->bulk_list[k]];
     for (int k = 0; k < net->nsurf; k++) ss += a[net->surface_list[k]];
@@ -365,7 +412,21 @@ int orc_run_model(const orc_network *net, int kind, const double *params, const 
                   double *phys_final, int timepoints, double *phys_traj, double *chem_traj, double *rates_traj,
                   int *nrows, double *dissipation_time, orc_stats *stats)
 {
+    return orc_run_model_pp(net, kind, params, y0, y_final, phys_final, timepoints, phys_traj, chem_traj, rates_traj,
+                            nrows, dissipation_time, stats, 0, NULL, 0);
+}
+
+/* ... and the postprocess model (wrap.f90:357-443): kind = UCLGPU_POSTPROCESS with a tracer history
+ * pp_grid[10][pp_ntime] (rows: time in s, density, gas T, dust T, radfield, zeta, N_H, N_H2, N_CO, N_C) */
+int orc_run_model_pp(const orc_network *net, int kind, const double *params, const double *y0, double *y_final,
+                     double *phys_final, int timepoints, double *phys_traj, double *chem_traj, double *rates_traj,
+                     int *nrows, double *dissipation_time, orc_stats *stats, int pp_ntime, const double *pp_grid,
+                     int pp_coldens)
+{
     orc_model *m = model_alloc(net, kind, params);
+    m->pp_ntime = pp_ntime;
+    m->pp_grid = pp_grid;
+    m->pp_coldens = (kind == UCLGPU_POSTPROCESS) ? pp_coldens : 0;
     const double *p = m->p;
     int neq = net->nspec + 1;
     int flag = 0;

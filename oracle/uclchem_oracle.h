@@ -93,6 +93,11 @@ int orc_run_model(const orc_network *net, int kind, const double *params, const 
                   double *phys_traj, double *chem_traj, double *rates_traj, int *nrows,
                   double *dissipation_time, orc_stats *stats);
 
+int orc_run_model_pp(const orc_network *net, int kind, const double *params, const double *y0, double *y_final,
+                     double *phys_final, int timepoints, double *phys_traj, double *chem_traj, double *rates_traj,
+                     int *nrows, double *dissipation_time, orc_stats *stats, int pp_ntime,
+                     const double *pp_grid /*[10][pp_ntime]*/, int pp_coldens);
+
 /* ncell independent models, params [nparam][ncell]; OpenMP over cells. */
 int orc_run_grid(const orc_network *net, int kind, int64_t ncell, const double *params,
                  const double *y0 /*[ncell][nspec+1] or NULL*/, double *y_final /*[ncell][nspec+1]*/,

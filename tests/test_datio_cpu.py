@@ -62,7 +62,7 @@ class _OracleBackedLibrary:
         self._nstat, self._iint = len(STAT_FIELDS), STAT_FIELDS.index("nintervals")
 
     def run_grid(self, kind, params, y0=None, timepoints=0, want_physics=False, want_chem=False, want_rates=False,
-                 step_budget=0, coefficients=None):
+                 step_budget=0, coefficients=None, pp_grid=None, pp_coldens=False):
         assert not coefficients, "the double has no per-reaction overrides"
         ncell = params.shape[1]
         tp = max(timepoints, 1)
@@ -77,7 +77,8 @@ class _OracleBackedLibrary:
             out["rates"] = np.zeros((ncell, timepoints + 1, self.nreac))
         for c in range(ncell):
             r = self.orc.run_model(kind, np.ascontiguousarray(params[:, c]), y0=None if y0 is None else y0[c],
-                                   timepoints=tp if timepoints else 500, rates=want_rates)
+                                   timepoints=tp if timepoints else 500, rates=want_rates,
+                                   pp_grid=None if pp_grid is None else pp_grid[c], pp_coldens=pp_coldens)
             out["y_final"][c], out["phys_final"][c], out["flag"][c] = r["y_final"], r["phys_final"], r["flag"]
             out["stats"][c, self._iint] = r["stats"]["nintervals"]
             out["dissipation_time"][c] = r["dissipation_time"]
@@ -211,3 +212,29 @@ def test_collapse_model_host_logic_and_oracle_physics(oracle, net, monkeypatch):
     # an unknown mode is a physics initialisation error (flag -2), never an exception
     from uclchem_b200.params import params_from_dict
     assert oracle.run_model(3, params_from_dict({"collapse_mode": 7})[:, 0])["flag"] == -2
+
+
+def test_postprocess_host_logic_and_oracle_physics(oracle, net, monkeypatch):
+    """uclchem.model.postprocess mirror (model.py:748-880) through the oracle-backed library double: one output row
+    per history point, physics rows taken from the history exactly as postprocess.f90:112-129 does (the row written
+    after interval k carries the values of history point k), Av from the supplied N_H (5.348e-22 N_H)."""
+    from uclchem_b200 import model
+    monkeypatch.setattr(model, "get_library", lambda *a, **k: _OracleBackedLibrary(oracle, net))
+    n, spy = 6, 3.16e7
+    t = np.linspace(0.0, 50.0, n) * spy
+    dens, tg, td = np.linspace(1e4, 2e4, n), np.linspace(10, 20, n), np.linspace(10, 15, n)
+    kw = dict(time_array=t, density_array=dens, gas_temperature_array=tg, dust_temperature_array=td,
+              zeta_array=np.full(n, 2.0), radfield_array=np.full(n, 1.5))
+    phys, chem, rates, start, flag = model.postprocess(param_dict={"initialDens": 1e4}, return_array=True, **kw)
+    assert flag == 0 and phys.shape == (n + 1, 1, 8) and chem.shape == (n + 1, 1, net.nspec)
+    assert np.allclose(phys[1:, 0, 0], t / spy + 1.0)                    # targets: history time + 1 yr (postprocess.f90:102)
+    assert np.allclose(phys[1:, 0, 1], dens) and np.allclose(phys[1:, 0, 2], tg) and np.allclose(phys[1:, 0, 3], td)
+    assert np.allclose(phys[1:, 0, 5], 1.5) and np.allclose(phys[1:, 0, 6], 2.0)
+    nh = np.linspace(1e21, 2e21, n)
+    phys2, _, _, _, flag2 = model.postprocess(param_dict={"initialDens": 1e4}, return_array=True, coldens_H_array=nh,
+                                             coldens_H2_array=0.4 * nh, coldens_CO_array=1e-5 * nh, coldens_C_array=1e-6 * nh, **kw)
+    assert flag2 == 0 and np.allclose(phys2[1:, 0, 4], float(np.float32(5.348e-22)) * nh)
+    with pytest.raises(ValueError, match="together"):
+        model.postprocess(return_array=True, coldens_H_array=nh, **kw)
+    with pytest.raises(AssertionError, match="same length"):
+        model.postprocess(return_array=True, **{**kw, "density_array": dens[:-1]})

@@ -41,6 +41,7 @@ class UclgpuOpts(C.Structure):
                 ("dissipation_time", _pd), ("reserved0", C.c_int32), ("step_budget", C.c_int32),
                 ("cost_hint", _pd), ("y0_index", _pi), ("ny0", C.c_int64),
                 ("n_coeff", C.c_int64), ("coeff_which", _pi), ("coeff_index", _pi), ("coeff_value", _pd),
+                ("pp_grid", _pd), ("pp_ntime", C.c_int32), ("pp_coldens", C.c_int32),
                 ("chunk_bytes", C.c_int64)]
 
 
@@ -114,7 +115,7 @@ class Library:
 
     def run_grid(self, kind: int, params: np.ndarray, y0=None, timepoints: int = 0, want_physics=False,
                  want_chem=False, want_rates=False, step_budget: int = 0, cost_hint=None,
-                 chunk_bytes: int = 0, y0_index=None, coefficients=None):
+                 chunk_bytes: int = 0, y0_index=None, coefficients=None, pp_grid=None, pp_coldens=False):
         params = np.ascontiguousarray(params, np.float64)
         assert params.ndim == 2 and params.shape[0] == NPARAM
         ncell = params.shape[1]
@@ -138,6 +139,10 @@ class Library:
         opts.timepoints = timepoints
         opts.step_budget = step_budget
         opts.chunk_bytes = chunk_bytes
+        if pp_grid is not None:   # postprocess: [ncell, 10, ntime] tracer histories
+            pp_grid = np.ascontiguousarray(pp_grid, np.float64)
+            assert pp_grid.ndim == 3 and pp_grid.shape[:2] == (ncell, 10)
+            opts.pp_grid, opts.pp_ntime, opts.pp_coldens = pp_grid.ctypes.data_as(_pd), pp_grid.shape[2], int(bool(pp_coldens))
         if coefficients:   # [(which, 0-based reaction, value), ...] with which in 0 alpha / 1 beta / 2 gamma
             cw = np.ascontiguousarray([c[0] for c in coefficients], np.int32)
             ci = np.ascontiguousarray([c[1] for c in coefficients], np.int32)

@@ -83,6 +83,10 @@ struct Scalars {
     double cs_dlength, cs_z1, cs_z2, cs_z3, cs_v0, cs_at, cs_vn0, cs_zn0, cs_dissipation_time, cs_max_temp,
         cs_drift_vel, cs_zn, cs_vn;
     int temp_indx;
+    // postprocess.f90 module state: this cell's tracer history [10][pp_ntime] (time s, density, gas T, dust T,
+    // radfield, zeta, N_H, N_H2, N_CO, N_C) in global memory, read by thread 0 at output times
+    const double *pp_grid;
+    int pp_ntime, pp_coldens, pp_tstep;
     // jshock.f90 module state
     double js_max_temp, js_vmin, js_tshock, js_tcool, js_max_dens, js_t_lambda, js_n_lambda, js_v0;
     // collapse.f90 module state

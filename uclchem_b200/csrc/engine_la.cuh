@@ -173,17 +173,21 @@ __device__ __noinline__ void rhs_eval(Smem &s, double *ydot)
         if (lane == 0) {
             const double d = y[NET_ID];
             const double h2col = 0.0 + 0.5 * y[NET_NH2] * d * (st.cloudsize / (double)1.0f);
+            // (postprocess tracers with supplied column densities keep the rates of calculateReactionRates:
+            // chemistry.f90:310-319)
             if (warp == NWARPS - 2) {
-                const double k = st.scat_h2_pre * h2_self_shielding_dev(h2col);
+                const double k = st.pp_coldens ? s.rate[NET_NR_H2_HV] : st.scat_h2_pre * h2_self_shielding_dev(h2col);
                 s.rate[NET_NR_H2_HV] = k;
                 const double f = k * y[NET_DEFERRED_RE_H2];
                 s.flux[NET_NR_H2_HV] = f;
                 st.dflux[0] = f;
             } else {
                 const double cocol = 0.0 + 0.5 * y[NET_NCO] * d * (st.cloudsize / (double)1.0f);
-                st.cocol = cocol;
-                st.h2col = h2col;
-                const double k = co_photo_rate_dev(h2col, cocol, st.radfield, st.av);
+                if (!st.pp_coldens) {
+                    st.cocol = cocol;
+                    st.h2col = h2col;
+                }
+                const double k = st.pp_coldens ? s.rate[NET_NR_CO_HV] : co_photo_rate_dev(h2col, cocol, st.radfield, st.av);
                 s.rate[NET_NR_CO_HV] = k;
                 const double f = k * y[NET_DEFERRED_RE_CO];
                 s.flux[NET_NR_CO_HV] = f;

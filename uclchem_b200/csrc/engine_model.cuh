@@ -34,6 +34,8 @@ struct RunArgs {
     int trace_cap, dump_at;
     int warm_restart;            // experimental (UCLGPU_WARM=1): keep the BDF history across output times
     long long max_steps;         // uclgpu_opts.step_budget: abandon a cell (flag -5) beyond this many BDF steps; 0 = off
+    const double *pp_grid;       // postprocess: [ncell][10][pp_ntime] tracer histories, or null
+    int pp_ntime, pp_coldens;
     const double *coef;          // [3][NREAC] overridden alpha / beta / gamma tables, or null
     const int *order;            // processing order of the cells (most expensive first) or null
     double *dump;
@@ -203,7 +205,7 @@ __device__ __noinline__ void jshock_update_physics_dev(Scalars &st)
 
 __device__ __noinline__ int initialize_physics_dev(Scalars &st)
 {
-    const double *p = st.p;
+    double *p = st.p;
     // coreInitializePhysics physics-core.f90:42-73
     st.time_in_years = st.current_time / C_SPY;
     st.cloudsize = (p[UCL_P_ROUT] - p[UCL_P_RIN]) * C_PC;
@@ -234,6 +236,27 @@ __device__ __noinline__ int initialize_physics_dev(Scalars &st)
         return collapse_initialize_t0(st);
     case UCLGPU_JSHOCK:
         return jshock_initialize_dev(st);
+    case UCLGPU_POSTPROCESS: { // postprocess.f90:24-92
+        if (!st.pp_grid || st.pp_ntime < 1) return -1;
+        const double *g = st.pp_grid;
+        const int n = st.pp_ntime;
+        if (st.pp_coldens) st.cloudsize = (double)0.f; // shielding column densities supplied separately
+        st.p[UCL_P_ENDATFINALDENSITY] = 0.0;
+        st.p[UCL_P_FREEFALL] = 0.0;
+        st.pp_tstep = 1;
+        st.target_time = g[0];
+        st.density = g[1 * n];
+        st.gastemp = g[2 * n];
+        st.dusttemp = g[3 * n];
+        st.radfield = g[4 * n];
+        st.zeta = g[5 * n];
+        if (st.pp_coldens) {
+            st.coldens = g[6 * n];
+            st.av = (double)5.348e-22f * st.coldens;
+        }
+        st.p[UCL_P_FINALTIME] = g[n - 1] / C_SPY;
+        return 0;
+    }
     }
     return -1;
 }
@@ -277,6 +300,10 @@ __device__ void update_target_time_dev(Scalars &st)
         else if (t * C_SPY < st.js_tshock) st.target_time = st.current_time + (double)0.05f * st.js_tshock;
         else st.target_time = (double)1.1f * st.current_time;
         break;
+    case UCLGPU_POSTPROCESS: // postprocess.f90:100-106
+        if (st.pp_tstep > st.pp_ntime) st.pp_tstep = st.pp_ntime; // guard: the Fortran would read past the array
+        st.target_time = st.pp_grid[st.pp_tstep - 1] + (double)1.f * C_SPY;
+        break;
     }
 }
 
@@ -308,6 +335,22 @@ __device__ void update_physics_dev(Scalars &st)
     case UCLGPU_JSHOCK:
         jshock_update_physics_dev(st);
         break;
+    case UCLGPU_POSTPROCESS: { // postprocess.f90:112-129
+        const double *g = st.pp_grid;
+        const int n = st.pp_ntime, k = st.pp_tstep - 1;
+        st.target_time = g[k];
+        st.density = g[1 * n + k];
+        st.gastemp = g[2 * n + k];
+        st.dusttemp = g[3 * n + k];
+        st.radfield = g[4 * n + k];
+        st.zeta = g[5 * n + k];
+        if (st.pp_coldens) {
+            st.coldens = g[6 * n + k];
+            st.av = (double)5.348e-22f * st.coldens;
+        }
+        st.pp_tstep = st.pp_tstep + 1;
+        break;
+    }
     default:
         break;
     }
@@ -478,6 +521,12 @@ __device__ void chemistry_setup_dev(Smem &s)
     st.h2col = 0.0 + (double)0.5f * a[NET_NH2] * st.density * cs;
     st.cocol = 0.0 + (double)0.5f * a[NET_NCO] * st.density * cs;
     st.ccol = 0.0 + (double)0.5f * a[NET_NC] * st.density * cs;
+    if (st.pp_coldens) { // chemistry.f90:183-189: postprocessed tracers have column densities provided
+        const int n = st.pp_ntime, k = st.pp_tstep - 1;
+        st.h2col = st.pp_grid[7 * n + k];
+        st.cocol = st.pp_grid[8 * n + k];
+        st.ccol = st.pp_grid[6 * n + k] * a[NET_NC];
+    }
     st.safe_mantle = fmax(1e-30, a[NET_IS]);
     st.safe_bulk = fmax(1e-30, a[NET_IB]);
     st.blr = fmin(1.0, NET_NSITES / (NET_GDR * st.safe_bulk));
@@ -565,6 +614,10 @@ __device__ void run_cell(Smem &s, Blk &b, const RunArgs &a, long long cell, long
     st.abstol_factor = st.p[UCL_P_ABSTOL_FACTOR];
     st.mxstep = (int)st.p[UCL_P_MXSTEP];
     st.step_budget = a.max_steps;
+    st.pp_ntime = a.pp_ntime;
+    st.pp_coldens = (a.kind == UCLGPU_POSTPROCESS) ? a.pp_coldens : 0;
+    st.pp_grid = a.pp_grid ? a.pp_grid + (size_t)cell * 10 * a.pp_ntime : nullptr;
+    st.pp_tstep = 1;
     st.c_alpha = a.coef ? a.coef : net_alpha;
     st.c_beta = a.coef ? a.coef + NREAC : net_beta;
     st.c_gama = a.coef ? a.coef + 2 * NREAC : net_gama;

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(NT, 1) k_probe(ProbeArgs a)
         st.use_tcrit = 0;
         st.step_budget = 0;
         st.c_alpha = net_alpha; st.c_beta = net_beta; st.c_gama = net_gama;
+        st.pp_grid = nullptr; st.pp_ntime = 0; st.pp_coldens = 0; st.pp_tstep = 1;
         st.cyc_rates = st.cyc_rhs = st.cyc_jac = st.cyc_factor = st.cyc_dense = st.cyc_solve = st.cyc_total = 0;
         initialize_physics_dev(st);
         T0_END
@@ -455,7 +456,7 @@ extern "C" int uclgpu_last_kernel_ms(int dev, double *ms, int64_t *launches)
 // D2H copy per array brings back exactly this chunk's rows and the host scatters them into the caller's arrays.
 struct DevBuf {
     int *y0_index = nullptr;
-    double *coef = nullptr;
+    double *coef = nullptr, *pp = nullptr;
     double *params = nullptr, *y0 = nullptr, *y_final = nullptr, *phys = nullptr, *ptraj = nullptr, *ctraj = nullptr,
            *rtraj = nullptr, *tdiss = nullptr;
     int32_t *flag = nullptr;
@@ -473,8 +474,8 @@ struct DevBuf {
     void release()
     {
         release_chunk();
-        cudaFree(params); cudaFree(y0); cudaFree(y0_index); cudaFree(coef);
-        params = y0 = nullptr; y0_index = nullptr; coef = nullptr;
+        cudaFree(params); cudaFree(y0); cudaFree(y0_index); cudaFree(coef); cudaFree(pp);
+        params = y0 = nullptr; y0_index = nullptr; coef = pp = nullptr;
     }
 };
 
@@ -491,7 +492,7 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
         if (rc) return rc;
     }
     if (ncell < 0 || ncell > INT32_MAX || !params || !y_final || !flag) return UCLGPU_ERR_BAD_ARGUMENT;
-    if ((int)kind < 0 || (int)kind > UCLGPU_JSHOCK) return UCLGPU_ERR_BAD_ARGUMENT;
+    if ((int)kind < 0 || (int)kind > UCLGPU_POSTPROCESS) return UCLGPU_ERR_BAD_ARGUMENT;
     if (ncell == 0) return 0;
     const int nd = (int)g_dev.size();
     const size_t T1 = opts ? (size_t)opts->timepoints + 1 : 0;
@@ -527,6 +528,7 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
             coef[(size_t)w * NREAC + r] = opts->coeff_value[k];
         }
     }
+    if (kind == UCLGPU_POSTPROCESS && !(opts && opts->pp_grid && opts->pp_ntime > 0)) return UCLGPU_ERR_BAD_ARGUMENT;
     const std::vector<int> ord = cost_order(params, ncell, opts ? opts->cost_hint : nullptr);
     // bytes of COMPACT result storage per cell on the device
     const size_t per_cell = sizeof(double) * (NEQ + UCLGPU_NPHYS + 1) + sizeof(int32_t) + sizeof(int) + sizeof(uclgpu_stats) +
@@ -553,6 +555,11 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
                     CK(cudaMalloc(&B.y0_index, sizeof(int) * ncell));
                     CK(cudaMemcpyAsync(B.y0_index, y0_index, sizeof(int) * ncell, cudaMemcpyHostToDevice, d.stream));
                 }
+            }
+            if (kind == UCLGPU_POSTPROCESS) {
+                const size_t nb = sizeof(double) * 10 * (size_t)opts->pp_ntime * ncell;
+                CK(cudaMalloc(&B.pp, nb));
+                CK(cudaMemcpyAsync(B.pp, opts->pp_grid, nb, cudaMemcpyHostToDevice, d.stream));
             }
             if (!coef.empty()) {
                 CK(cudaMalloc(&B.coef, sizeof(double) * coef.size()));
@@ -590,7 +597,7 @@ extern "C" int uclgpu_run_grid(uclgpu_model_kind kind, int64_t ncell, const doub
                 RunArgs a;
                 memset(&a, 0, sizeof(a));
                 a.kind = (int)kind; a.ncell = ncell; a.nrun = (long long)n; a.compact = 1; a.order = B.order;
-                a.params = B.params; a.y0 = B.y0; a.y0_index = B.y0_index; a.coef = B.coef; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
+                a.params = B.params; a.y0 = B.y0; a.y0_index = B.y0_index; a.coef = B.coef; a.pp_grid = B.pp; a.pp_ntime = opts ? opts->pp_ntime : 0; a.pp_coldens = opts ? opts->pp_coldens : 0; a.y_final = B.y_final; a.phys_final = B.phys; a.flag = B.flag; a.stats = B.stats;
                 if (opts) {
                     a.max_steps = opts->step_budget;
                     a.timepoints = opts->timepoints;

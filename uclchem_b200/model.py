@@ -80,7 +80,7 @@ def _format_output(n_out, abunds, success_flag):
 
 
 def _run_single(kind, param_dict, out_species, return_array, return_dataframe, return_rates, starting_chemistry,
-                timepoints, extra):
+                timepoints, extra, **run_kw):
     lib = get_library()
     pd_ = _lower(param_dict)
     traj = return_array or return_dataframe
@@ -113,13 +113,14 @@ def _run_single(kind, param_dict, out_species, return_array, return_dataframe, r
     want_rows = traj or any(k in files for k in ("outputfile", "columnfile", "ratefile"))
     want_rates = (traj and return_rates) or "ratefile" in files
     out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if want_rows else 0,
-                       want_physics=want_rows, want_chem=want_rows, want_rates=want_rates, coefficients=coefficients)
+                       want_physics=want_rows, want_chem=want_rows, want_rates=want_rates, coefficients=coefficients,
+                       **run_kw)
     while not traj and want_rows and int(out["flag"][0]) == -6 and timepoints < (1 << 20):
         # disk mode has no row limit in the reference (rows go straight to the file, io.f90:59-83): the rows come
         # back through the in-memory buffers here, so a model with more output intervals is re-run with more room
         timepoints *= 4
         out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints, want_physics=True, want_chem=True,
-                           want_rates=want_rates, coefficients=coefficients)
+                           want_rates=want_rates, coefficients=coefficients, **run_kw)
     flag = int(out["flag"][0])
     tdiss = float(out["dissipation_time"][0]) if flag >= 0 else None   # model.py:606-607
     if not traj:
@@ -223,11 +224,40 @@ def jshock(shock_vel, param_dict=None, out_species=None, return_array=False, ret
                        starting_chemistry, timepoints, {"shock_vel": shock_vel})
 
 
+def _tracer_history(time_array, density_array, gas_temperature_array, dust_temperature_array, zeta_array,
+                    radfield_array, coldens_H_array, coldens_H2_array, coldens_CO_array, coldens_C_array):
+    """[..., 10, ntime] history block of the C ABI from the reference's postprocess arguments (model.py:748-830:
+    every array must have the length of time_array; times are in seconds like the reference's `timegrid`)."""
+    t = np.asarray(time_array, dtype=np.float64)
+    cols = [coldens_H_array, coldens_H2_array, coldens_CO_array, coldens_C_array]
+    use = coldens_H_array is not None
+    if use and any(c is None for c in cols):
+        raise ValueError("coldens_H_array, coldens_H2_array, coldens_CO_array and coldens_C_array must be given together")
+    rows = [t, density_array, gas_temperature_array, dust_temperature_array, radfield_array, zeta_array]
+    rows += cols if use else [np.zeros_like(t)] * 4
+    for r in rows:
+        assert r is not None and np.shape(r) == t.shape, "All arrays must be the same length"
+    return np.stack([np.asarray(r, dtype=np.float64) for r in rows], axis=-2), use
+
+
+def postprocess(param_dict=None, out_species=None, return_array=False, return_dataframe=False, return_rates=False,
+                starting_chemistry=None, time_array=None, density_array=None, gas_temperature_array=None,
+                dust_temperature_array=None, zeta_array=None, radfield_array=None, coldens_H_array=None,
+                coldens_H2_array=None, coldens_CO_array=None, coldens_C_array=None):
+    """Chemistry along a supplied tracer history (model.py:748-880, postprocess.f90): density, temperatures, radiation
+    field and cosmic-ray rate -- and optionally the shielding column densities -- are read from the arrays at every
+    time of `time_array` (seconds); one output row per history point."""
+    grid, use = _tracer_history(time_array, density_array, gas_temperature_array, dust_temperature_array, zeta_array,
+                                radfield_array, coldens_H_array, coldens_H2_array, coldens_CO_array, coldens_C_array)
+    return _run_single("postprocess", param_dict, out_species, return_array, return_dataframe, return_rates,
+                       starting_chemistry, grid.shape[-1], {}, pp_grid=grid[None], pp_coldens=use)
+
+
 # ---------------------------------------------------------------------------------------
 # grids: what scripts/grid.py does with a process pool, in one call
 # ---------------------------------------------------------------------------------------
 def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None, return_array=False,
-              return_rates=False, timepoints=TIMEPOINTS):
+              return_rates=False, timepoints=TIMEPOINTS, **run_kw):
     lib = get_library()
     pd_ = _lower(param_dict)
     file_keys = [k for k in pd_ if k.endswith("file")]
@@ -247,7 +277,7 @@ def _run_grid(kind, param_dict, starting_chemistry, extra, out_species=None, ret
         y0[:, : lib.nspec] = sc[:, : lib.nspec]
     out = lib.run_grid(MODEL_KINDS[kind], params, y0=y0, timepoints=timepoints if return_array else 0,
                        want_physics=return_array, want_chem=return_array, want_rates=return_array and return_rates,
-                       coefficients=coefficients)
+                       coefficients=coefficients, **run_kw)
     res = {"flag": out["flag"], "abundances": out["y_final"][:, : lib.nspec], "physics": out["phys_final"],
            "stats": out["stats"], "species": lib.species}
     if return_array:
@@ -303,3 +333,17 @@ def jshock_grid(shock_vel, param_dict, starting_chemistry=None, out_species=None
                 return_rates=False, timepoints=TIMEPOINTS):
     return _run_grid("jshock", param_dict, starting_chemistry, {"shock_vel": shock_vel}, out_species, return_array,
                      return_rates, timepoints)
+
+
+def postprocess_grid(param_dict, time_array, density_array, gas_temperature_array, dust_temperature_array, zeta_array,
+                     radfield_array, coldens_H_array=None, coldens_H2_array=None, coldens_CO_array=None,
+                     coldens_C_array=None, starting_chemistry=None, out_species=None, return_array=False,
+                     return_rates=False):
+    """A table of tracers in one call: every history array is [ncell, ntime] (all tracers share ntime)."""
+    grid, use = _tracer_history(time_array, density_array, gas_temperature_array, dust_temperature_array, zeta_array,
+                                radfield_array, coldens_H_array, coldens_H2_array, coldens_CO_array, coldens_C_array)
+    assert grid.ndim == 3, "history arrays must be [ncell, ntime]"
+    pd_ = dict(param_dict or {})
+    pd_.setdefault("initialDens", grid[:, 1, 0])     # one parameter column of the right length fixes ncell
+    return _run_grid("postprocess", pd_, starting_chemistry, {}, out_species, return_array, return_rates, grid.shape[-1],
+                     pp_grid=grid, pp_coldens=use)

@@ -46,7 +46,7 @@ _IGNORED = {
 # REAL(dp) :: x = <single-precision literal>  ->  value is float32-rounded
 _F32_DEFAULTS = {"rout": 0.05, "fhe": 0.1, "epsilon": 0.01, "uv_yield": 0.03}
 
-MODEL_KINDS = {"cloud": 0, "hot_core": 1, "cshock": 2, "collapse": 3, "jshock": 4}
+MODEL_KINDS = {"cloud": 0, "hot_core": 1, "cshock": 2, "collapse": 3, "jshock": 4, "postprocess": 5}
 
 
 def default_params(ncell: int = 1) -> np.ndarray:
