@@ -84,9 +84,13 @@ def test_every_key_of_the_reference_parser_is_accounted_for():
         "ebmaxuvcr", "uv_yield", "metallicity", "omega", "reltol", "abstol_factor", "abstol_min", "jacobian",
         "abundsavefile", "abundloadfile", "outputfile", "ratefile", "fluxfile", "columnfile", "fh", "ntime",
         "trajecfile"]
-    # not offered by the GPU path: per-reaction alpha/beta/gamma overrides (rate tables are compiled into the
-    # library), the user-Jacobian switch (the Jacobian is always analytic) and the postprocess trajectory inputs
+    # not parameter COLUMNS: the per-reaction alpha/beta/gamma dictionaries (taken out of the dictionary by
+    # uclchem_b200.model and passed as uclgpu_opts.coeff_*), the user-Jacobian switch (the Jacobian is always
+    # analytic) and the legacy postprocess file inputs (model.postprocess takes arrays, like the reference's)
     unsupported = {"alpha", "beta", "gamma", "jacobian", "ntime", "trajecfile"}
+    from uclchem_b200.model import _coefficients
+    pd_ = {"alpha": {3: 1e-9}, "gamma": {10: 5.0, 11: 6.0}, "zeta": 2.0}
+    assert _coefficients(pd_) == [(0, 2, 1e-9), (2, 9, 5.0), (2, 10, 6.0)] and pd_ == {"zeta": 2.0}
     for k in parser_keys:
         if k in unsupported:
             with pytest.raises(KeyError):

@@ -22,9 +22,11 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 # per-network build options: dense-tail threshold of the symbolic LU and extra defines.  The crp-photo
 # network (config 5) needs the compact shared-memory layout and a slightly smaller dense block to fit
-# the 227 KB of an SM; its library is built and compile-checked, not yet run on a B200.
+# the 227 KB of an SM.
 TAG_OPTIONS = {
     "crp_photo": {"dense_threshold": 0.95, "defines": ["-DUCLGPU_COMPACT_SMEM"]},
+    # default network + grain-assisted recombination (tools/make_gar_network.py): default layout and options
+    "gar": {},
 }
 
 
