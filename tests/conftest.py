@@ -31,8 +31,10 @@ def _built_libraries():
     import shutil
     from uclchem_b200 import build
     from uclchem_b200._capi import library_path
-    if not library_path("default").exists() and (shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists()):
-        build.compile("default")
+    if shutil.which("nvcc") or Path("/usr/local/cuda/bin/nvcc").exists():
+        for tag in ("default", "crp_photo", "gar"):
+            if not library_path(tag).exists():
+                build.compile(tag)
     from oracle import oracle as orc
     orc.build()
 
