@@ -22,7 +22,9 @@ def _states(n=4):
 def test_rate_coefficients_match_oracle(lib, oracle):
     """calculateReactionRates (rates.f90:21-343) per cell: <= 1e-12 relative, same zero pattern."""
     ys = _states()
-    for pd_ in (STATIC, dict(STATIC, initialTemp=30.0, zeta=10.0, radfield=3.0, baseAv=1.0)):
+    for pd_ in (STATIC, dict(STATIC, initialTemp=30.0, zeta=10.0, radfield=3.0, baseAv=1.0),
+                dict(STATIC, initialTemp=200.0, initialDens=1e6, zeta=100.0, radfield=10.0, baseAv=0.5),
+                dict(STATIC, initialTemp=60.0, cosmicRayAttenuation=True, ionModel="H", improvedH2CRPDissociation=True)):
         p1 = params_from_dict(pd_)
         got = lib.get_rates(np.repeat(p1, len(ys), axis=1), ys)
         for k in range(len(ys)):
@@ -437,3 +439,20 @@ def test_postprocess_model_against_oracle(lib, oracle):
     assert res[0] == 0 and res[1] > 0
     grid = model.postprocess_grid({"initialDens": [1e4, 3e3]}, g[:, 0], g[:, 1], g[:, 2], g[:, 3], g[:, 5], g[:, 4], out_species=["CO"])
     assert (grid["flag"] == 0).all() and grid["out_species"][0, 0] == pytest.approx(res[1], rel=1e-12)
+
+
+def test_cosmic_ray_attenuation_models_against_oracle(lib, oracle):
+    """physics-core.f90:121-157 (ionizationDependency): column-density dependent H2 cosmic-ray dissociation rate for
+    both ionisation models, refreshed after every output interval; free fall makes the column grow with time."""
+    p = params_from_dict({"initialDens": [1e3, 1e4], "finalDens": 1e6, "freefall": True, "endAtFinalDensity": False,
+                          "initialTemp": 15.0, "finalTime": 3e5, "cosmicRayAttenuation": True, "ionModel": ["L", "H"],
+                          "improvedH2CRPDissociation": True, "zeta": [1.0, 5.0]})
+    out = lib.run_grid(0, p, step_budget=300000)
+    ref, pf, flag, _ = oracle.run_grid(0, p, nthreads=2)
+    assert (out["flag"] == 0).all() and (flag == 0).all()
+    for c in range(2):
+        np.testing.assert_allclose(out["phys_final"][c, :7], pf[c, :7], rtol=1e-6)
+        assert max_dex(out["y_final"][c, :335], ref[c, :335]) < DEX_TOL, c
+    # the reference refuses improvedH2CRPDissociation without cosmicRayAttenuation (physics-core.f90:60-64)
+    bad = params_from_dict({"improvedH2CRPDissociation": True, "finalTime": 1.0})
+    assert lib.run_grid(0, bad)["flag"][0] == -2
