@@ -408,7 +408,29 @@ class Config5(Workload):
 WORKLOADS = {1: Config1, 2: Config2, 3: Config3, 4: Config4, 5: Config5}
 
 
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly ONE JSON line (the driver parses it): everything else that libraries print there
+    (NCCL's version banner, for one) goes to stderr from here on; emit_json writes to the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=NSLICE)
@@ -458,11 +480,11 @@ def main():
         cpu = cpu_baseline_dict(r, cores, seconds)
         workload["step"] = (f"one continuous {seconds:.0f} s sample of the first step's cells (shuffled work queue, all cores busy), "
                             f"reported as {a.steps} equal steps")
-        print(json.dumps({
+        emit_json({
             "impl": "reference", "metric": METRIC, "value": r["rate"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * r["wall"] / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload, "cpu_baseline": cpu,
-            "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+            "e2e": {"value": r["rate"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -682,7 +704,7 @@ def main():
                                        if hinted_steps else "none (generic longest-first order)")
         if a.workload == 1:
             line["single_model_seconds"] = kernel_ms / 1e3 / a.steps
-        print(json.dumps(line), flush=True)
+        emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -591,3 +591,7 @@ int orc_get_odes(const orc_network *net, const double *params, const double *y_i
     model_free(m);
     return flag;
 }
+
+/* Experiment hook support (debug only, see orc_vode.c): the frozen rate coefficients of the model a DVODE callback
+ * is running in (ctx of the RHS is the orc_model). */
+const double *orc_ctx_rate(void *ctx) { return ((orc_model *)ctx)->rate; }

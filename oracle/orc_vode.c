@@ -304,9 +304,25 @@ static void vjust(vode_t *s, int iord)
     }
 }
 
+/* Experiment hook (debug only, tools/study_engine_linalg.py; never set by tests or bench): replaces the dense
+ * finite-difference Jacobian + LINPACK LU by callbacks, so that the engine's linear algebra (table emulator) can be
+ * run inside this DVODE on the CPU.  setup(ctx, y, gamma, fresh) -> 0 ok / 1 singular; solve(ctx, b) in place. */
+static orc_la_setup g_la_setup = NULL;
+static orc_la_solve g_la_solve = NULL;
+void orc_set_linalg_hook(orc_la_setup setup, orc_la_solve solve) { g_la_setup = setup; g_la_solve = solve; }
+
 /* DVJAC dvode.f90:8182 (MITER=2, JSV=1, not JACSP) */
 static int vjac(vode_t *s)
 {
+    if (g_la_setup) {
+        int fresh = 0;
+        if (s->nst == 0 || s->nst > s->nslj + s->msbj) fresh = 1;
+        if (s->icf == 1 && s->drc < s->ccmxj) fresh = 1;
+        if (s->icf == 2) fresh = 1;
+        if (fresh) { s->nslj = s->nst; s->jcur = 1; s->nje++; } else s->jcur = 0;
+        s->nlu++;
+        return g_la_setup(s->ctx, s->y, s->h * s->rl1, fresh);
+    }
     int n = s->n;
     size_t lenp = (size_t)n * n;
     double hrl1 = s->h * s->rl1;
@@ -376,7 +392,7 @@ static int vnls(vode_t *s, int *nflag)
         for (;;) { /* label 30/40 */
             for (int i = 0; i < n; i++)
                 y[i] = (s->rl1 * s->h) * savf[i] - (s->rl1 * yh2[i] + acor[i]);
-            dgesl(s->wm, n, s->ipvt, y);
+            if (g_la_solve) g_la_solve(s->ctx, y); else dgesl(s->wm, n, s->ipvt, y);
             s->nni++;
             if (fabs(s->rc - 1.0) > 0.0) {
                 double cscale = 2.0 / (1.0 + s->rc);

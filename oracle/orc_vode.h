@@ -30,6 +30,11 @@ int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double to
 /* Wall-clock guard for bounded benchmark samples (NOT part of the reference algorithm): after
  * orc_set_deadline(seconds) every model still running `seconds` from now stops with
  * ORC_FLAG_DEADLINE.  0 switches the guard off (default). */
+/* Experiment hook (debug only): see orc_vode.c */
+typedef int (*orc_la_setup)(void *ctx, const double *y, double gamma, int fresh);
+typedef void (*orc_la_solve)(void *ctx, double *b);
+void orc_set_linalg_hook(orc_la_setup setup, orc_la_solve solve);
+
 #define ORC_FLAG_DEADLINE (-98)
 void orc_set_deadline(double seconds_from_now);
 int orc_deadline_expired(void);

@@ -102,8 +102,9 @@ def test_static_clouds_match_the_oracle_in_result_and_in_work(lib2, oracle2, net
 def test_reference_tolerances_of_this_network_on_quiet_cells(lib2, oracle2, net2):
     """The reference's own test of this network loosens the tolerances to reltol 1e-5 / abstol_min 1e-15
     (tests/test_photo_on_grain.py:112-113).  On cold, quiet cells the engine follows the oracle there too.  (On hot,
-    dense, strongly irradiated cells it does not: the Newton matrix I - gamma J is factorised without pivoting, and at
-    the step sizes a loose tolerance allows it loses the accuracy the corrector needs -- DESIGN.md section 9.)"""
+    dense, strongly irradiated cells NEITHER arm is reproducible at abstol_min = 1e-15: bulk O dips negative within
+    the tolerance and the reference's own `@O + @O -> @O2` term, y' = -2 k y^2, blows up in finite time -- diagnosed
+    with the CPU harness tools/study_engine_linalg.py)"""
     from uclchem_b200.params import params_from_dict
     p = params_from_dict({"initialDens": [1e4, 1e5], "initialTemp": [10.0, 20.0], "finalTime": 1e3, "reltol": 1e-5,
                           "abstol_min": 1e-15})
