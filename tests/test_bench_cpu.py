@@ -77,3 +77,27 @@ def test_json_line_assembly():
     assert line["solver"]["steps_per_model"] == 8000 and line["cpu_baseline"]["kind"] == "port"
     for key in ("metric", "steps", "warmup", "higher_is_better", "vs_baseline", "data", "config", "clocks", "parity"):
         assert key in line
+
+
+def test_cost_hint_comes_from_the_zeta_neighbours_only():
+    """The bench returns to the same cells every NSLICE steps; the hint it passes to uclgpu_opts.cost_hint must never be a
+    cell's own cost from that earlier visit (nobody integrates the same model twice), only what a sweep over the grid
+    knows: the measured cost of the nearest zeta neighbours inside the same (density, temperature) row."""
+    w = bench.Config2(0, 1, argparse.Namespace(cells=0))
+    att = np.full(10000, np.nan)
+    assert w.cost_hint(0, att) is None                       # first step: nothing known
+    att[w.slices[0]] = 1000.0 + np.arange(2500)              # step 0 measured
+    h1 = w.cost_hint(1, att)                                 # step 1: flat index 4k+1, left neighbour 4k is measured
+    assert np.array_equal(h1, 1000.0 + np.arange(2500))
+    att[w.slices[1]] = 7.0
+    h0 = w.cost_hint(4, att)                                 # the bench comes back to slice 0: own 1000+ values must not appear
+    assert (h0 == 7.0).all()
+    # neighbours never cross a row boundary: cell 20 (zeta index 0 of its row) must not see cell 19 (last zeta of the previous row)
+    att[:] = np.nan
+    att[19] = 5.0e4
+    att[21] = 3.0
+    assert w.cost_hint(0, att)[w.slices[0].tolist().index(20)] == 3.0
+    # the larger of the two nearest neighbours wins (a stalled neighbour is the better warning)
+    att[:] = np.nan
+    att[101], att[103] = 9.0e4, 8.0e3
+    assert w.cost_hint(2, att)[w.slices[2].tolist().index(102)] == 9.0e4
