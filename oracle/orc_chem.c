@@ -657,6 +657,11 @@ void orc_init_desfrac(orc_model *m)
     }
 }
 
+/* Experiment switch (debug only, tools/study_frozen_branch.py; 0 in every test and bench run = the reference's
+ * rule): +1 / -1 force the mantle-growth / mantle-loss branch of the three-phase transfer regardless of the sign
+ * of the uncorrected surface growth.  Not thread safe: single-model studies only. */
+int g_orc_force_branch = 0;
+
 /* GETYDOT, odes.f90:6-5181, as a walk over the MakeRates rules */
 void orc_getydot(const orc_network *net, const double *rate, const double *y, double blr,
                  double surface_coverage, double safe_mantle, double safe_bulk, double dens, double *ydot,
@@ -703,7 +708,7 @@ void orc_getydot(const orc_network *net, const double *rate, const double *y, do
     if (surfgrowth_uncorrected) *surfgrowth_uncorrected = ss;
     /* three-phase transfer, odes.f90:4815-5153 (species order: surface block, then bulk block) */
     int nrefr = net->n_refractory;
-    if (ydot[iS] < 0) {
+    if (g_orc_force_branch ? g_orc_force_branch < 0 : ydot[iS] < 0) {
         surface_coverage = fmin(1.0, safe_bulk / safe_mantle);
         for (int k = 0; k < net->nsurf; k++) {
             int s = net->surface_list[k], b = net->bulk_list[k];

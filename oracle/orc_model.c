@@ -595,3 +595,4 @@ int orc_get_odes(const orc_network *net, const double *params, const double *y_i
 /* Experiment hook support (debug only, see orc_vode.c): the frozen rate coefficients of the model a DVODE callback
  * is running in (ctx of the RHS is the orc_model). */
 const double *orc_ctx_rate(void *ctx) { return ((orc_model *)ctx)->rate; }
+double orc_ctx_surfgrowth(void *ctx) { return ((orc_model *)ctx)->surfgrowth; }

@@ -362,6 +362,11 @@ static int vjac(vode_t *s)
     return ier != 0 ? 1 : 0;
 }
 
+/* Experiment hook (debug only): called with phase 0 before and phase 1 after the first RHS evaluation of every
+ * corrector pass (label 10 of DVNLSD), see tools/study_frozen_branch.py. */
+static orc_pass_hook g_pass_hook = NULL;
+void orc_set_pass_hook(orc_pass_hook h) { g_pass_hook = h; }
+
 /* DVNLSD dvode.f90:7926 */
 static int vnls(vode_t *s, int *nflag)
 {
@@ -377,7 +382,9 @@ static int vnls(vode_t *s, int *nflag)
         int m = 0;
         double delp = 0.0, del = 0.0;
         memcpy(y, yh1, n * sizeof(double));
+        if (g_pass_hook) g_pass_hook(s->ctx, 0);
         s->f(s->ctx, s->tn, y, savf);
+        if (g_pass_hook) g_pass_hook(s->ctx, 1);
         s->nfe++;
         if (s->ipup > 0) {
             int ierpj = vjac(s);
@@ -686,6 +693,7 @@ int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double to
     int n = s->n;
     s->f = f;
     s->ctx = ctx;
+    if (g_pass_hook) g_pass_hook(ctx, 0);
     s->rtol = rtol;
     s->atol = atol;
     if (fabs(tout - *t) <= 0.0) return 1; /* :5995-5999: returns with ISTATE unchanged */

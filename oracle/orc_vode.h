@@ -34,6 +34,8 @@ int vode_solve(vode_t *s, vode_rhs f, void *ctx, double *y, double *t, double to
 typedef int (*orc_la_setup)(void *ctx, const double *y, double gamma, int fresh);
 typedef void (*orc_la_solve)(void *ctx, double *b);
 void orc_set_linalg_hook(orc_la_setup setup, orc_la_solve solve);
+typedef void (*orc_pass_hook)(void *ctx, int phase);
+void orc_set_pass_hook(orc_pass_hook h);
 
 #define ORC_FLAG_DEADLINE (-98)
 void orc_set_deadline(double seconds_from_now);

@@ -14,7 +14,8 @@ print = functools.partial(print, flush=True)
 tag = sys.argv[1]
 dens, temp, zeta, tfin, rt, am = (float(a) for a in sys.argv[2:8])
 mode = sys.argv[8] if len(sys.argv) > 8 else "engine"
-os.environ["ORC_TRACE"] = f"/tmp/study_{tag}_{mode}.txt"
+if not os.environ.get("STUDY_NO_TRACE"):
+    os.environ["ORC_TRACE"] = f"/tmp/study_{tag}_{mode}.txt"
 from oracle.oracle import Oracle
 from uclchem_b200 import symbolic
 from uclchem_b200.network import Network
@@ -103,7 +104,9 @@ def solve(ctx, bp):
 cb = (SETUP(setup), SOLVE(solve))
 if mode != "plain":
     orc.lib.orc_set_linalg_hook(cb[0], cb[1])
-p = params_from_dict({"initialDens": dens, "initialTemp": temp, "zeta": zeta, "finalTime": tfin, "reltol": rt, "abstol_min": am})
+import json
+p = params_from_dict(dict({"initialDens": dens, "initialTemp": temp, "zeta": zeta, "finalTime": tfin, "reltol": rt, "abstol_min": am},
+                          **json.loads(os.environ.get("STUDY_EXTRA", "{}"))))   # e.g. the config-2 grid: {"radfield": 1.0, "baseAv": 2.0, "rout": 0.05}
 t0 = time.time()
 orc.set_deadline(float(os.environ.get("STUDY_SECONDS", "600")))
 r = orc.run_model(0, p[:, 0])
