@@ -542,6 +542,15 @@ static void vstep(vode_t *s)
         dsm = s->acnrm / s->tq[2];
         if (dsm <= 1.0) break;
         /* label 100 */
+        if (s->trace && getenv("ORC_TRACE_ETF")) { /* debug: which component fails the error test */
+            int im = 0;
+            double vm = 0.0;
+            for (int i = 0; i < n; i++) {
+                double v = fabs(s->acor[i] * s->ewt[i]);
+                if (v > vm) { vm = v; im = i; }
+            }
+            fprintf((FILE *)s->trace, "ETF %.10e %.4e %d %d %.4e %.4e %.4e %.4e\n", s->tn, s->h, s->nq, im, vm, dsm, s->acor[im], s->y[im]);
+        }
         s->kflag--;
         s->netf++;
         nflag = -2;
