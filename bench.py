@@ -6,10 +6,13 @@ cosmic-ray rates, 1 Myr each, default network), ALL of its cells.  With N ranks 
 (25 x 20 x 20N points, rank r owns every N-th zeta plane), so per-GPU work is fixed (weak scaling), the job
 integrates N x 10^4 distinct models, and rank 0 gathers every model's final abundances and flag.
 
-A *step* is one call of the hot path over one batch: an interleaved quarter of the rank's grid (cells whose flat
-index is congruent to step mod 4: every density and temperature, every fourth zeta), 2 500 models per GPU; four
-consecutive steps cover the grid once.  (A whole pass is ~35 s, and the driver's `--steps 20 --warmup 5` has to
-finish in minutes; a quarter keeps ~17 cells per SM in the work queue.)
+A *step* is one call of the hot path over one batch: an interleaved quarter of the rank's grid (cells with
+(density index + zeta index) mod 4 == step mod 4: every density, temperature and zeta in every step), 2 500 models
+per GPU; four consecutive steps are one pass over the grid.  (A whole pass is ~40 s, and the driver's `--steps 20
+--warmup 5` has to finish in minutes; a quarter keeps ~17 cells per SM in the work queue.)  From the second step
+of a pass on the call carries `uclgpu_opts.cost_hint`: per cell the largest step count measured on its neighbouring
+grid cells EARLIER IN THE SAME PASS (what a user who integrates a grid in a few chunks knows); nothing is carried
+from one pass to the next, and a cell's own earlier integration is never used.
 
 The reference algorithm does not terminate in bounded work on ~1 % of these cells: the three-phase surface/bulk
 transfer has a kink at zero net surface growth, DVODE hits MXSTEP in every retry there, and UCLCHEM's own stall
@@ -79,6 +82,34 @@ def config2_params(ncell_side=(25, 20, 20), rank=0, world=1):
 def slice_cells(ncell, q, nslice=NSLICE):
     """Cells of step slice q: flat index congruent to q (mod nslice)."""
     return np.arange(q % nslice, ncell, nslice)
+
+
+GRID_SHAPE = (25, 20, 20)   # config 2: densities x temperatures x zetas of one rank's grid (flat index, zeta fastest)
+
+
+def checkerboard_slices(shape=GRID_SHAPE, nslice=NSLICE):
+    """Config-2 steps: slice q holds the cells with (density index + zeta index) mod nslice == q.  Every slice sees
+    every density, temperature and zeta (2 500 cells each), and every cell of slices 1..3 has density / zeta
+    neighbours in the slices integrated before it in the same pass over the grid."""
+    nd, nt, nz = shape
+    D, _, Z = np.meshgrid(np.arange(nd), np.arange(nt), np.arange(nz), indexing="ij")
+    lab = ((D + Z) % nslice).ravel()
+    return [np.where(lab == q)[0] for q in range(nslice)]
+
+
+def neighbourhood_max(values, shape=GRID_SHAPE):
+    """Per cell the largest finite entry of `values` (flat, NaN = unknown) among its 26 neighbours in the
+    (density, temperature, zeta) index box, the cell itself excluded; NaN where no neighbour is known."""
+    nd, nt, nz = shape
+    pad = np.full((nd + 2, nt + 2, nz + 2), -np.inf)
+    pad[1:-1, 1:-1, 1:-1] = np.where(np.isnan(values), -np.inf, values).reshape(shape)
+    best = np.full(shape, -np.inf)
+    for a in (0, 1, 2):
+        for b in (0, 1, 2):
+            for c in (0, 1, 2):
+                if (a, b, c) != (1, 1, 1):
+                    best = np.maximum(best, pad[a:a + nd, b:b + nt, c:c + nz])
+    return np.where(np.isinf(best), np.nan, best).ravel()
 
 
 class ClockSampler:
@@ -294,40 +325,30 @@ class Config2(Workload):
         if a.cells:
             self.params = np.ascontiguousarray(self.params[:, np.linspace(0, self.params.shape[1] - 1, a.cells).astype(int)])
         n = self.params.shape[1]
-        self.nzeta = n if a.cells else 20   # cells per (density, temperature) row of the rank's grid
-        self.slices = [slice_cells(n, q) for q in range(NSLICE)]
+        self.grid = not a.cells     # the regular 25 x 20 x 20 grid (False: debug subset, flat slicing, no hint)
+        self.slices = checkerboard_slices() if self.grid else [slice_cells(n, q) for q in range(NSLICE)]
         self.desc = {"workload": "config[1]: 10^4-point static cloud grid (25 n_H x 20 T x 20 zeta), 1 Myr, default network "
                                  "335 species / 3203 reactions, reltol 1e-8, ALL cells"
                                  + (f"; {world} ranks: zeta axis refined to {20 * world} points, one 10^4-cell grid per GPU" if world > 1 else ""),
-                     "step": f"one interleaved quarter of the rank's grid ({len(self.slices[0])} cells per GPU, flat index = step mod {NSLICE}); "
-                             f"{NSLICE} consecutive steps cover the grid once",
+                     "step": f"one interleaved quarter of the rank's grid ({len(self.slices[0])} cells per GPU: (density index + zeta index) mod {NSLICE} "
+                             f"= step mod {NSLICE}, every density, temperature and zeta in every step); {NSLICE} consecutive steps are one pass over the grid",
                      "cells_per_gpu_per_step": int(len(self.slices[0])), "cells_total": int(world * n)}
 
     def step(self, k):
         return StepSpec(0, self.params[:, self.slices[k % NSLICE]])
 
     def cost_hint(self, k, attempts):
-        """Expected cost of the cells of step k from what is already known about the grid: `attempts` holds, per
-        flat grid index, the BDF step attempts of the cells integrated so far (NaN = not yet).  A cell's zeta
-        neighbours (flat index -1 / +1 inside the same (density, temperature) row) belong to the previous / next
-        slice, so from the second step on every cell has a measured neighbour; the hint is the larger of the two
-        nearest measured neighbours, cells without one get the median.  This is what a user sweeping a grid plane
-        by plane can do with `uclgpu_opts.cost_hint`; the first step runs without.  A cell's OWN earlier visit is
-        never used, although the bench comes back to the same cells every NSLICE steps: a user integrates a model
-        once, and knowing its exact cost from an identical earlier run would be an artefact of the benchmark loop."""
-        idx = self.slices[k % NSLICE]
-        n = len(attempts)
-        nz = self.nzeta
-        h = np.full(len(idx), np.nan)
-        for d in (1, 2, 3):
-            cand = []
-            for sgn in (-1, 1):
-                nb = idx + sgn * d
-                ok = (nb >= 0) & (nb < n) & (np.clip(nb, 0, n - 1) // nz == idx // nz)
-                cand.append(np.where(ok, attempts[np.clip(nb, 0, n - 1)], np.nan))
-            both = np.vstack(cand)
-            best = np.where(np.isnan(both).all(axis=0), np.nan, np.nanmax(np.where(np.isnan(both), -np.inf, both), axis=0))
-            h = np.where(np.isnan(h), best, h)
+        """Expected cost of the cells of step k from what THIS pass over the grid has measured so far: `attempts`
+        holds, per flat grid index, the BDF step attempts of the cells integrated since the pass began (NaN = not
+        yet; the caller forgets everything when a new pass begins).  The hint of a cell is the largest figure among
+        its 26 neighbours in the (density, temperature, zeta) index box -- the cells on which DVODE stalls form
+        bands along the density axis, so a stalled neighbour is a good warning -- and the median where no
+        neighbour is known.  The first step of every pass runs without a hint (generic longest-first order of the
+        library).  This is what a user who integrates a large grid in a few chunks can do with
+        `uclgpu_opts.cost_hint`; nothing is ever taken from an earlier integration of the same model or grid."""
+        if not self.grid or np.isnan(attempts).all():
+            return None
+        h = neighbourhood_max(attempts)[self.slices[k % NSLICE]]
         if np.isnan(h).all():
             return None
         return np.where(np.isnan(h), np.nanmedian(h), h)
@@ -454,7 +475,7 @@ def main():
                          "default: the workload's own (about ten times what a typical model of the workload needs)")
     ap.add_argument("--cpu-seconds", type=float, default=60.0, help="bound of the cpu_baseline sample")
     ap.add_argument("--no-cost-hint", action="store_true",
-                    help="do not pass uclgpu_opts.cost_hint (measured step counts of the neighbouring zeta plane, workload 2)")
+                    help="do not pass uclgpu_opts.cost_hint (step counts measured on neighbouring grid cells earlier in the same pass, workload 2)")
     ap.add_argument("--cells", type=int, default=0, help="debug: override the grid size (not a valid bench line)")
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -616,9 +637,13 @@ def main():
         t0 = time.perf_counter()
         for k in range(a.steps):
             b = steps[step_id(k) % wl.nslice]
+            if step_id(k) % wl.nslice == 0:
+                attempts[:] = np.nan    # a new pass over the grid: nothing from the previous one is used
             hint = wl.cost_hint(step_id(k), attempts) if not a.no_cost_hint else None
             hinted_steps += hint is not None
             ms, nl = b.run(a.step_budget, hint)
+            if os.environ.get("UCLCHEM_BENCH_VERBOSE"):
+                log(f"rank {rank} step {k}: kernel {ms / 1e3:.2f} s, {'hinted' if hint is not None else 'no hint'}")
             if len(attempts):
                 attempts[wl.slices[step_id(k) % NSLICE]] = b.main.stats.numpy()[:, i_att].sum(axis=1)
             kernel_ms += ms
@@ -711,7 +736,7 @@ def main():
                              traffic=traffic, stat_fields=STAT_FIELDS, per_rank_kernel_ms=per_rank,
                              gather_bytes=(world - 1) * n_max * (neq + 1) * 8 if world > 1 else 0)
         line["config"]["cost_hint"] = (f"{hinted_steps} of {a.steps} steps ran with uclgpu_opts.cost_hint = step attempts measured on the "
-                                       "nearest zeta neighbours (same density and temperature) in an earlier step of this run, never on the cell itself (the first step has none)"
+                                       "neighbouring grid cells (26-cell index box) earlier in the SAME pass over the grid; the first step of every pass has none, and nothing is carried from one pass to the next"
                                        if hinted_steps else "none (generic longest-first order)")
         if a.workload == 1:
             line["single_model_seconds"] = kernel_ms / 1e3 / a.steps

@@ -14,11 +14,16 @@ from uclchem_b200.params import PARAM_INDEX
 def test_workload_is_the_whole_config2_grid_in_four_interleaved_steps():
     p = bench.config2_params()
     assert p.shape[1] == 25 * 20 * 20
-    sl = [bench.slice_cells(p.shape[1], q) for q in range(bench.NSLICE)]
+    sl = bench.Config2(0, 1, argparse.Namespace(cells=0)).slices
     assert sorted(np.concatenate(sl).tolist()) == list(range(10000)) and all(len(s) == 2500 for s in sl)
-    # every slice sees every density and temperature
+    # every slice sees every density, temperature and zeta
     for s in sl:
         assert len(np.unique(p[PARAM_INDEX["initialdens"], s])) == 25 and len(np.unique(p[PARAM_INDEX["initialtemp"], s])) == 20
+        assert len(np.unique(p[PARAM_INDEX["zeta"], s])) == 20
+    # ... and slice q holds the cells with (density index + zeta index) mod 4 == q: density / zeta neighbours are in other slices
+    D, T, Z = np.unravel_index(np.arange(10000), bench.GRID_SHAPE)
+    for q, s in enumerate(sl):
+        assert ((D[s] + Z[s]) % bench.NSLICE == q).all()
     # N ranks: the zeta axis is refined N-fold and dealt round-robin; rank grids are disjoint, same density/temperature axes
     z = [np.unique(bench.config2_params(rank=r, world=4)[PARAM_INDEX["zeta"]]) for r in range(4)]
     allz = np.sort(np.concatenate(z))
@@ -79,25 +84,40 @@ def test_json_line_assembly():
         assert key in line
 
 
-def test_cost_hint_comes_from_the_zeta_neighbours_only():
-    """The bench returns to the same cells every NSLICE steps; the hint it passes to uclgpu_opts.cost_hint must never be a
-    cell's own cost from that earlier visit (nobody integrates the same model twice), only what a sweep over the grid
-    knows: the measured cost of the nearest zeta neighbours inside the same (density, temperature) row."""
+def test_cost_hint_comes_from_neighbouring_cells_of_the_same_pass_only():
+    """The hint the bench passes to uclgpu_opts.cost_hint for a cell is the largest step-attempt count among its 26
+    neighbours in the (density, temperature, zeta) index box that were integrated EARLIER IN THE SAME PASS over the
+    grid -- never the cell's own cost (the bench returns to the same cells every NSLICE steps; nobody integrates the
+    same model twice), and main() forgets everything when a new pass begins."""
     w = bench.Config2(0, 1, argparse.Namespace(cells=0))
+    flat = np.arange(10000).reshape(bench.GRID_SHAPE)
     att = np.full(10000, np.nan)
-    assert w.cost_hint(0, att) is None                       # first step: nothing known
-    att[w.slices[0]] = 1000.0 + np.arange(2500)              # step 0 measured
-    h1 = w.cost_hint(1, att)                                 # step 1: flat index 4k+1, left neighbour 4k is measured
-    assert np.array_equal(h1, 1000.0 + np.arange(2500))
-    att[w.slices[1]] = 7.0
-    h0 = w.cost_hint(4, att)                                 # the bench comes back to slice 0: own 1000+ values must not appear
-    assert (h0 == 7.0).all()
-    # neighbours never cross a row boundary: cell 20 (zeta index 0 of its row) must not see cell 19 (last zeta of the previous row)
+    assert w.cost_hint(0, att) is None                       # first step of a pass: nothing known
+    att[w.slices[0]] = 100.0
+    c = flat[10, 7, 3]                                       # (10 + 3) mod 4 = 1: a cell of slice 1
+    assert c in w.slices[1]
+    att[flat[11, 7, 3]] = 9.0e4                              # density neighbour, (11 + 3) mod 4 = 2 ... pretend it is known
+    att[flat[10, 8, 4]] = 5.0e3
+    h1 = w.cost_hint(1, att)
+    assert h1[w.slices[1].tolist().index(c)] == 9.0e4       # the largest neighbour wins
+    att[c] = 1.0e6                                           # the cell's OWN figure is never its hint
+    assert w.cost_hint(1, att)[w.slices[1].tolist().index(c)] == 9.0e4
+    # neighbours do not wrap around the grid edges: cell (0, 0, 0) must not see (24, 19, 19)
     att[:] = np.nan
-    att[19] = 5.0e4
-    att[21] = 3.0
-    assert w.cost_hint(0, att)[w.slices[0].tolist().index(20)] == 3.0
-    # the larger of the two nearest neighbours wins (a stalled neighbour is the better warning)
-    att[:] = np.nan
-    att[101], att[103] = 9.0e4, 8.0e3
-    assert w.cost_hint(2, att)[w.slices[2].tolist().index(102)] == 9.0e4
+    att[flat[24, 19, 19]] = 7.0e4
+    att[flat[1, 1, 1]] = 3.0
+    assert w.cost_hint(0, att)[w.slices[0].tolist().index(flat[0, 0, 0])] == 3.0
+    # cells without a known neighbour get the median of the known hints
+    h = w.cost_hint(2, att)
+    assert np.isfinite(h).all()
+    # neighbourhood_max itself: brute force on random data
+    rng = np.random.default_rng(0)
+    v = np.where(rng.random(10000) < 0.3, rng.random(10000), np.nan)
+    got = bench.neighbourhood_max(v).reshape(bench.GRID_SHAPE)
+    V = v.reshape(bench.GRID_SHAPE)
+    for (i, j, k) in [(0, 0, 0), (24, 19, 19), (5, 6, 7), (12, 0, 19), (24, 10, 0)]:
+        box = [V[a, b, c] for a in range(max(0, i - 1), min(25, i + 2)) for b in range(max(0, j - 1), min(20, j + 2))
+               for c in range(max(0, k - 1), min(20, k + 2)) if (a, b, c) != (i, j, k) and not np.isnan(V[a, b, c])]
+        assert (np.isnan(got[i, j, k]) and not box) or got[i, j, k] == max(box)
+    # the debug subset (--cells) has no grid structure: no hint
+    assert bench.Config2(0, 1, argparse.Namespace(cells=50)).cost_hint(1, np.ones(50)) is None
